@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- region-scored triplets/s for CORE's region pooling / scoring / loss path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward + backward of the region path over one batch of synthetic triplets
+(BASELINE.json config[1]: 16 triplets x 64 candidate 1024x1024 masks per GPU, bf16 features):
+mask resample + validity sums, region pooling (fg, bg and all candidates), L2-normalise, fg/bg
+cosine losses, region x query InfoNCE (negatives all-gathered across ranks), segmentation loss,
+and the backward of all of it.  Prints ONE JSON line (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "region_scored_triplets_per_sec"
+UNIT = "triplets/s"
+CFG = dict(B=16, M=64, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, tau=0.07)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ inputs
+def device_inputs(dev, seed, cfg, mask_dtype):
+    """Seeded synthetic triplets generated on the device (SURVEY 8d recipe: union of rectangles and
+    an ellipse per mask, 1 in 32 empty, 1 in 256 full; mask 0 of every image is the GT)."""
+    B, M, H, W = cfg["B"], cfg["M"], cfg["H"], cfg["W"]
+    g = torch.Generator(device=dev).manual_seed(seed)
+    emb = torch.randn(B, cfg["C"], cfg["h"], cfg["w"], device=dev, generator=g).bfloat16()
+    comb = torch.nn.functional.normalize(torch.randn(B, 1, cfg["C"], device=dev, generator=g), dim=-1)
+    pred = torch.nn.functional.avg_pool2d(2 * torch.randn(B, 1, cfg["hp"] + 4, cfg["wp"] + 4, device=dev, generator=g), 5, 1) * 5
+    pred = pred.bfloat16()
+    masks = torch.zeros(B, M, H, W, device=dev, dtype=torch.float32)
+    yy = torch.arange(H, device=dev, dtype=torch.float32)[:, None]
+    xx = torch.arange(W, device=dev, dtype=torch.float32)[None, :]
+    r = torch.rand(B, M, 8, device=dev, generator=g).cpu().numpy()
+    for b in range(B):
+        for m in range(M):
+            i = b * M + m
+            if i % 32 == 31:
+                continue
+            if i % 256 == 129:
+                masks[b, m] = 1.0
+                continue
+            side = float(np.sqrt(0.005 + 0.295 * r[b, m, 0]))
+            rh, rw = max(2, int(H * side * (0.4 + 0.6 * r[b, m, 1]))), max(2, int(W * side * (0.4 + 0.6 * r[b, m, 2])))
+            y0, x0 = int(r[b, m, 3] * (H - rh)), int(r[b, m, 4] * (W - rw))
+            masks[b, m, y0:y0 + rh, x0:x0 + rw] = 1.0
+            cy, cx = (0.2 + 0.6 * r[b, m, 5]) * H, (0.2 + 0.6 * r[b, m, 6]) * W
+            ry, rx = max(2.0, H * side * 0.4), max(2.0, W * side * 0.4)
+            masks[b, m][((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0] = 1.0
+    if mask_dtype == "u8":
+        masks = (masks * 255).to(torch.uint8)
+    return {"pred": pred, "emb": emb, "comb": comb, "masks": masks}
+
+
+# -------------------------------------------------------------------------------------- clock probe
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------- CPU baseline leg
+def cpu_port_step(sample, tau):
+    """One fwd+bwd of the same step on the host cores through the ATen port of the reference."""
+    from oracle import aten_port as ap
+    p, e, c = (sample[k].detach().clone().requires_grad_(True) for k in ("pred", "emb", "comb"))
+    loss, _ = ap.region_step_loss(p, e, c, sample["masks"], tau=tau)
+    loss.backward()
+    return float(loss.detach())
+
+
+def cpu_baseline(inputs_cpu, cfg, triplets, iters, warm=1):
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sample = {k: (v[:triplets].float() if v.is_floating_point() else v[:triplets].float() / 255.0) for k, v in inputs_cpu.items()}
+    for _ in range(warm):
+        cpu_port_step(sample, cfg["tau"])
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        cpu_port_step(sample, cfg["tau"])
+        ts.append(time.perf_counter() - t0)
+    med = sorted(ts)[len(ts) // 2]
+    return {"value": triplets / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{triplets} triplets x {cfg['M']} masks {cfg['H']}x{cfg['W']} fp32, fwd+bwd, median of {iters} after {warm} warm-up "
+                      f"({med * 1e3:.0f} ms/step); oracle/aten_port.py = reference ATen op sequence"}, med
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    triplets = args.cpu_triplets
+    host = device_inputs(torch.device("cpu"), 1234, dict(cfg, B=triplets), "f32")
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sample = {k: v.float() for k, v in host.items()}
+    for _ in range(args.warmup):
+        cpu_port_step(sample, cfg["tau"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_step(sample, cfg["tau"])
+    dt = (time.perf_counter() - t0) / args.steps
+    val = triplets / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, args, sample_triplets=triplets),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"each step = {triplets} triplets x {cfg['M']} masks (bounded sample of the {cfg['B']}-triplet batch), "
+                                       "reference ATen op sequence (oracle/aten_port.py; the reference is Python and cannot travel)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(cfg, args, sample_triplets=None):
+    c = {"workload": f"CORE fwd+bwd region path, batch {cfg['B']} triplets x {cfg['M']} masks per GPU, "
+                     f"{cfg['H']}x{cfg['W']} {args.mask_dtype} masks, bf16 features [B,{cfg['C']},{cfg['h']},{cfg['w']}], "
+                     f"logits [B,1,{cfg['hp']},{cfg['wp']}] (BASELINE.json configs[1])",
+         "triplets_per_gpu": cfg["B"], "masks_per_triplet": cfg["M"], "feature_map": [cfg["C"], cfg["h"], cfg["w"]],
+         "mask_size": [cfg["H"], cfg["W"]], "mask_dtype": args.mask_dtype, "tau": cfg["tau"], "backward": True,
+         "emb_grad": True, "negatives": "all-gathered across ranks (NCCL)",
+         "l2": "inputs (>= 1 GiB of masks per step) exceed the 126 MB L2; no explicit flush"}
+    if sample_triplets is not None:
+        c["cpu_sample_triplets"] = sample_triplets
+    return c
+
+
+# --------------------------------------------------------------------------------------------- main
+def main():
+    ap_ = argparse.ArgumentParser()
+    ap_.add_argument("--gpus", type=int, default=1)
+    ap_.add_argument("--steps", type=int, default=20)
+    ap_.add_argument("--warmup", type=int, default=3)
+    ap_.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap_.add_argument("--mask-dtype", default="f32", choices=["f32", "u8"])
+    ap_.add_argument("--batch", type=int, default=CFG["B"])
+    ap_.add_argument("--masks", type=int, default=CFG["M"])
+    ap_.add_argument("--cpu-triplets", type=int, default=1, help="triplets per CPU-baseline step (bounded sample)")
+    ap_.add_argument("--cpu-iters", type=int, default=3)
+    ap_.add_argument("--no-cpu-baseline", action="store_true")
+    ap_.add_argument("--pool-engine", default="auto")
+    ap_.add_argument("--sim-engine", default="auto")
+    args = ap_.parse_args()
+    cfg = dict(CFG, B=args.batch, M=args.masks)
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch.distributed as dist
+    from cor_b200 import ops, region
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, tc_peak, peak_kind = peaks()
+
+    inp = device_inputs(dev, 1234 + rank, cfg, args.mask_dtype)
+    kw = dict(tau=cfg["tau"], gather=world > 1, pool_engine=args.pool_engine, sim_engine=args.sim_engine)
+
+    def step_device():
+        p = inp["pred"].detach().requires_grad_(True)
+        c = inp["comb"].detach().requires_grad_(True)
+        e = inp["emb"].detach().requires_grad_(True)
+        out = region.region_step(p, e, c, inp["masks"], **kw)
+        out.loss.backward()
+        return out.loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- CPU baseline first (rank 0, N=1 only), on a bounded sample of the same tensors
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        host_small = {k: v[:args.cpu_triplets].cpu() for k, v in inp.items()}
+        cpu, _ = cpu_baseline(host_small, cfg, args.cpu_triplets, args.cpu_iters)
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ops.TIMING["events"] = {}
+    n0 = ops.LAUNCHES["count"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step_device()
+        e1.record()
+        barrier()
+    launches = ops.LAUNCHES["count"] - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    events, ops.TIMING["events"] = ops.TIMING["events"], None
+    per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in events.items()}   # ms per step
+    calls = {k: len(v) // args.steps for k, v in events.items()}
+    ms_step = ms_total / args.steps
+    value = cfg["B"] * world / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (mask_prep: one pass over the full-resolution masks)
+    esz = 4 if args.mask_dtype == "f32" else 1
+    n_masks, P = cfg["B"] * cfg["M"], cfg["h"] * cfg["w"]
+    w32_written = True     # backward needs the fp32 weights (emb_grad)
+    prep_bytes = n_masks * cfg["H"] * cfg["W"] * esz + n_masks * P * (2 + (4 if w32_written else 0)) + n_masks * 16
+    dom = max(per_kernel, key=per_kernel.get)
+    prep_ms = per_kernel.get("cor_mask_prep", 0.0) / max(1, calls.get("cor_mask_prep", 1))
+    achieved = prep_bytes / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0
+    roofline = {"kernel": "mask_prep_kernel (cor_mask_prep)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                "algorithmic_bytes_per_launch": prep_bytes, "ms_per_launch": prep_ms, "share_of_step": per_kernel.get("cor_mask_prep", 0.0) / ms_step,
+                "dominant_by_events": dom}
+
+    # ---- end to end through the public API with host buffers (H2D of the step's inputs + D2H of the loss)
+    bufs = region.StepBuffers(cfg["B"], cfg["M"], cfg["C"], cfg["h"], cfg["w"], cfg["H"], cfg["W"], cfg["hp"], cfg["wp"], device=dev,
+                              mask_dtype=inp["masks"].dtype)
+    host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in inp.items()}
+    for k in host:
+        host[k].copy_(inp[k])
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        bufs.run(host, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(e2e_steps):
+        bufs.run(host, **kw)
+    s1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) / e2e_steps
+    e2e_ms = torch.tensor([max(s0.elapsed_time(s1) / e2e_steps, wall * 1e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = cfg["B"] * world / (float(e2e_ms) * 1e-3)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": workload_config(cfg, args), "clocks": clk.summary(),
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": bufs.h2d_bytes, "d2h_bytes_per_step": 4,
+                        "ms_per_step": float(e2e_ms), "steps": e2e_steps},
+                "gpu_launches": launches, "roofline": roofline,
+                "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
+                "loss": float(loss)}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,238 @@
+// mask_prep: one pass over full-resolution masks producing
+//   (1) the bilinear (align_corners=False) resample to the feature grid  -- replaces F.interpolate at
+//       mask_adapter.py:19-20 / loss_func.py:46-47 (ATen upsample_bilinear2d),
+//   (2) sum(mask) and sum(1-mask) over the FULL-resolution mask -- the validity tests of
+//       loss_func.py:73-74 and :103-107,
+//   (3) the pooling denominators sum_p w.
+// HBM-bound streaming kernel: every mask byte is read exactly once with 128-bit no-allocate loads;
+// the 4 taps per output pixel hit lines the same CTA streams.  Deterministic: per-CTA partials in
+// double, reduced in fixed order by a second tiny kernel.
+#include "common.cuh"
+
+namespace cor {
+
+template <typename T>
+struct VecSum;  // sums a 16-byte vector of T into (sum m) and count
+
+template <>
+struct VecSum<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void add(uint4 v, float& s) {
+    s += (__uint_as_float(v.x) + __uint_as_float(v.y)) + (__uint_as_float(v.z) + __uint_as_float(v.w));
+  }
+};
+template <>
+struct VecSum<bf16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void add(uint4 v, float& s) {
+    s += ((bf16lo(v.x) + bf16hi(v.x)) + (bf16lo(v.y) + bf16hi(v.y))) + ((bf16lo(v.z) + bf16hi(v.z)) + (bf16lo(v.w) + bf16hi(v.w)));
+  }
+};
+template <>
+struct VecSum<uint8_t> {
+  static constexpr int N = 16;
+  __device__ static __forceinline__ void add(uint4 v, float& s) {
+    // exact integer byte sum (<= 16*255), added to an fp32 accumulator of integers < 2^24 per thread
+    unsigned t = __dp4a(v.x, 0x01010101u, 0u);
+    t = __dp4a(v.y, 0x01010101u, t);
+    t = __dp4a(v.z, 0x01010101u, t);
+    t = __dp4a(v.w, 0x01010101u, t);
+    s += (float)t;
+  }
+};
+
+__device__ __forceinline__ float apply_transform(float r, int transform) {
+  if (transform == COR_W_CLAMP) return fminf(fmaxf(r, 0.f), 1.f);
+  if (transform == COR_W_SIGMOID) return sigmoid_acc(r);
+  return r;
+}
+
+// grid.x = n_masks * chunks.  CTA (n, chunk) owns output rows [r0, r1) and input rows [i0, i1).
+template <typename T, bool kNeedOneMinus>
+__global__ void __launch_bounds__(256) mask_prep_kernel(const T* __restrict__ masks, float mscale, int Hm, int Wm, int h,
+                                                        int w, int chunks, int transform, float* __restrict__ w_f32,
+                                                        bf16* __restrict__ w_bf16, long long ldw, int group,
+                                                        long long group_stride, double* __restrict__ part) {
+  const int n = blockIdx.x / chunks, chunk = blockIdx.x % chunks;
+  const int r0 = (int)((long long)chunk * h / chunks), r1 = (int)((long long)(chunk + 1) * h / chunks);
+  const long long i0 = (long long)r0 * Hm / h, i1 = (long long)r1 * Hm / h;
+  const T* base = masks + (long long)n * Hm * Wm;
+
+  // ---- part A: stream input rows [i0, i1) for the full-resolution sums -------------------------
+  const T* p = base + i0 * Wm;
+  const long long cnt = (i1 - i0) * Wm;
+  constexpr int VE = VecSum<T>::N;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};   // 4 independent accumulators (ILP)
+  float s1m = 0.f;                     // sum(1 - m) for float types when values may exceed [0,1]
+  long long head = ((16 - ((uintptr_t)p & 15)) & 15) / sizeof(T);
+  if (head > cnt) head = cnt;
+  for (long long i = threadIdx.x; i < head; i += blockDim.x) {
+    float v = to_f<T>(p[i]);
+    s[0] += v;
+    if (kNeedOneMinus) s1m += 1.f - v * mscale;
+  }
+  const long long nvec = (cnt - head) / VE;
+  const uint4* pv = reinterpret_cast<const uint4*>(p + head);
+  long long i = threadIdx.x;
+  for (; i + 3 * (long long)blockDim.x < nvec; i += 4 * (long long)blockDim.x) {
+    uint4 a = ld_stream16(pv + i), b = ld_stream16(pv + i + blockDim.x), c = ld_stream16(pv + i + 2 * blockDim.x),
+          d = ld_stream16(pv + i + 3 * blockDim.x);
+    VecSum<T>::add(a, s[0]);
+    VecSum<T>::add(b, s[1]);
+    VecSum<T>::add(c, s[2]);
+    VecSum<T>::add(d, s[3]);
+    if (kNeedOneMinus) {
+      // float masks outside [0,1] (contract violation) still get the reference's exact predicate
+      const float* f;
+      f = reinterpret_cast<const float*>(&a); s1m += (1.f - f[0] * mscale) + (1.f - f[1] * mscale) + (1.f - f[2] * mscale) + (1.f - f[3] * mscale);
+      f = reinterpret_cast<const float*>(&b); s1m += (1.f - f[0] * mscale) + (1.f - f[1] * mscale) + (1.f - f[2] * mscale) + (1.f - f[3] * mscale);
+      f = reinterpret_cast<const float*>(&c); s1m += (1.f - f[0] * mscale) + (1.f - f[1] * mscale) + (1.f - f[2] * mscale) + (1.f - f[3] * mscale);
+      f = reinterpret_cast<const float*>(&d); s1m += (1.f - f[0] * mscale) + (1.f - f[1] * mscale) + (1.f - f[2] * mscale) + (1.f - f[3] * mscale);
+    }
+  }
+  for (; i < nvec; i += blockDim.x) {
+    uint4 a = ld_stream16(pv + i);
+    VecSum<T>::add(a, s[0]);
+    if (kNeedOneMinus) {
+      const float* f = reinterpret_cast<const float*>(&a);
+      s1m += (1.f - f[0] * mscale) + (1.f - f[1] * mscale) + (1.f - f[2] * mscale) + (1.f - f[3] * mscale);
+    }
+  }
+  for (long long j = head + nvec * VE + threadIdx.x; j < cnt; j += blockDim.x) {
+    float v = to_f<T>(p[j]);
+    s[0] += v;
+    if (kNeedOneMinus) s1m += 1.f - v * mscale;
+  }
+
+  // ---- part B: resample output rows [r0, r1) --------------------------------------------------
+  const float sh = (float)Hm / (float)h, sw = (float)Wm / (float)w;
+  float den = 0.f, den16 = 0.f;
+  const int nout = (r1 - r0) * w;
+  for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+    const int r = r0 + o / w, x = o % w;
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    src_index(sh, r, Hm, y0, y1, ly0, ly1);
+    src_index(sw, x, Wm, x0, x1, lx0, lx1);
+    const T* row0 = base + (long long)y0 * Wm;
+    const T* row1 = base + (long long)y1 * Wm;
+    const float v00 = to_f<T>(__ldg(row0 + x0)), v01 = to_f<T>(__ldg(row0 + x1));
+    const float v10 = to_f<T>(__ldg(row1 + x0)), v11 = to_f<T>(__ldg(row1 + x1));
+    const float rv = (ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11)) * mscale;
+    const long long pix = (long long)r * w + x;
+    const long long off = (long long)(n / group) * group_stride + (long long)(n % group) * ldw + pix;
+    if (w_f32) w_f32[(long long)n * ldw + pix] = rv;
+    const float tv = apply_transform(rv, transform);
+    den += tv;
+    if (w_bf16) {
+      const bf16 q = __float2bfloat16_rn(tv);
+      w_bf16[off] = q;
+      den16 += __bfloat162float(q);
+    }
+  }
+
+  __shared__ double scratch[4 * 32];
+  double v[4];
+  v[0] = ((double)s[0] + (double)s[1]) + ((double)s[2] + (double)s[3]);
+  v[1] = (double)s1m;
+  v[2] = (double)den;
+  v[3] = (double)den16;
+  block_sum<4>(v, scratch);
+  if (threadIdx.x == 0) {
+    double* o = part + (long long)blockIdx.x * 4;
+    o[0] = v[0];
+    o[1] = kNeedOneMinus ? v[1] : (double)cnt;   // element count when sum(1-m) is derived exactly
+    o[2] = v[2];
+    o[3] = v[3];
+  }
+}
+
+// stats[n] = {sum m, sum (1-m), den, den_bf16}; fixed-order reduction of the chunk partials.
+__global__ void mask_prep_reduce_kernel(const double* __restrict__ part, int n_masks, int chunks, float mscale,
+                                        int one_minus_direct, float* __restrict__ stats) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_masks) return;
+  double a = 0, b = 0, c = 0, d = 0;
+  for (int k = 0; k < chunks; ++k) {
+    const double* o = part + ((long long)n * chunks + k) * 4;
+    a += o[0]; b += o[1]; c += o[2]; d += o[3];
+  }
+  float* s = stats + (long long)n * 4;
+  const double sm = a * (double)mscale;
+  s[0] = (float)sm;
+  // one_minus_direct 1: b is sum(1-m) accumulated directly (f32 masks);
+  //                  0: b is the element count, sum(1-m) = count - sum (bf16 masks);
+  //                  2: u8 masks, exact integers: (count*vmax - sum_bytes) * scale with vmax = round(1/scale)
+  double om;
+  if (one_minus_direct == 1) om = b;
+  else if (one_minus_direct == 2) om = (b * (double)lrintf(1.0f / mscale) - a) * (double)mscale;
+  else om = b - sm;
+  s[1] = (float)fmax(om, 0.0);
+  s[2] = (float)c;
+  s[3] = (float)d;
+}
+
+static int pick_chunks(int n_masks, int Hm, int Wm, int h, size_t esize) {
+  long long target = (long long)sm_count() * 8;
+  long long chunks = (target + n_masks - 1) / n_masks;
+  long long by_bytes = ((long long)Hm * Wm * (long long)esize) / 16384;
+  if (by_bytes < 1) by_bytes = 1;
+  if (chunks > by_bytes) chunks = by_bytes;
+  if (chunks > h) chunks = h;
+  if (chunks > Hm) chunks = Hm;
+  if (chunks < 1) chunks = 1;
+  return (int)chunks;
+}
+
+}  // namespace cor
+
+using namespace cor;
+
+extern "C" size_t cor_mask_prep_work_bytes(int n_masks, int Hm, int Wm, int h, int w) {
+  (void)w;
+  // upper bound independent of dtype: chunks <= h
+  return (size_t)n_masks * (size_t)(h > 0 ? h : 1) * 4 * sizeof(double);
+}
+
+extern "C" int cor_mask_prep(const void* masks, int mask_dtype, float mask_scale, int n_masks, int Hm, int Wm, int h,
+                             int w, int transform, float* w_f32, void* w_bf16, long long ldw, int group,
+                             long long group_stride, float* stats, void* work, cor_stream_t stream) {
+  COR_REQUIRE(masks && stats && work, "cor_mask_prep: null pointer");
+  COR_REQUIRE(n_masks > 0 && Hm > 0 && Wm > 0 && h > 0 && w > 0, "cor_mask_prep: bad shape n=%d %dx%d -> %dx%d", n_masks,
+              Hm, Wm, h, w);
+  COR_REQUIRE(ldw >= (long long)h * w, "cor_mask_prep: ldw %lld < h*w", ldw);
+  COR_REQUIRE(transform >= 0 && transform <= 2, "cor_mask_prep: bad transform %d", transform);
+  if (group <= 0) { group = 1; group_stride = ldw; }
+  COR_REQUIRE(group_stride >= (long long)group * ldw, "cor_mask_prep: group_stride %lld < group*ldw", group_stride);
+  const size_t es = mask_dtype == COR_F32 ? 4 : mask_dtype == COR_BF16 ? 2 : 1;
+  const int chunks = pick_chunks(n_masks, Hm, Wm, h, es);
+  COR_REQUIRE((long long)n_masks * chunks < 2147483647LL, "cor_mask_prep: grid too large");
+  dim3 grid((unsigned)(n_masks * chunks));
+  cudaStream_t st = as_stream(stream);
+  double* part = reinterpret_cast<double*>(work);
+  int direct = 1;
+  switch (mask_dtype) {
+    case COR_F32:
+      mask_prep_kernel<float, true><<<grid, 256, 0, st>>>((const float*)masks, mask_scale, Hm, Wm, h, w, chunks, transform,
+                                                          w_f32, (bf16*)w_bf16, ldw, group, group_stride, part);
+      break;
+    case COR_BF16:
+      // bf16 masks: sum(1-m) from count - sum (bf16 values are exact in fp32; partial sums < 2^24 ulp-safe
+      // for the > 0 predicate only when m in [0,1], which a bf16 mask operand already assumes)
+      mask_prep_kernel<bf16, false><<<grid, 256, 0, st>>>((const bf16*)masks, mask_scale, Hm, Wm, h, w, chunks, transform,
+                                                          w_f32, (bf16*)w_bf16, ldw, group, group_stride, part);
+      direct = 0;
+      break;
+    case COR_U8:
+      mask_prep_kernel<uint8_t, false><<<grid, 256, 0, st>>>((const uint8_t*)masks, mask_scale, Hm, Wm, h, w, chunks,
+                                                             transform, w_f32, (bf16*)w_bf16, ldw, group, group_stride, part);
+      direct = 2;
+      break;
+    default:
+      COR_REQUIRE(false, "cor_mask_prep: unsupported mask dtype %d", mask_dtype);
+  }
+  int rc = check_launch("mask_prep_kernel");
+  if (rc) return rc;
+  mask_prep_reduce_kernel<<<ceil_div(n_masks, 128), 128, 0, st>>>(part, n_masks, chunks, mask_scale, direct, stats);
+  return check_launch("mask_prep_reduce_kernel");
+}

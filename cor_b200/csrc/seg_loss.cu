@@ -1,0 +1,242 @@
+// Segmentation loss: weighted BCE + weighted IoU with the 31x31 box-filter edge weight
+// (utils/loss_func.py:5-32), with the target resample of utils/trainer_v3_g.py:67 fused in.
+//
+// One CTA per 64x64 logit tile.  The (resampled) target incl. a 15-pixel zero-padded halo is built
+// once in shared memory (4 taps per value straight from the full-resolution mask), the box filter is
+// separable sliding-window sums in shared memory, and the per-pixel terms are reduced in registers ->
+// warp shuffles -> one partial record per tile.  Compulsory HBM traffic only: logits once, the mask
+// sectors the taps touch once; ~15 full passes over [B,1,256,256] in the eager reference become one.
+#include "common.cuh"
+
+namespace cor {
+
+constexpr int kT = 64;            // tile edge
+constexpr int kHalo = 15;         // (31-1)/2
+constexpr int kTH = kT + 2 * kHalo;   // 94
+constexpr int kTS = kTH + 1;      // padded row stride (odd -> conflict-free column walks)
+constexpr int kHS = kT + 1;
+constexpr int kNP = 8;            // partial sums per tile
+
+struct SegSmem {
+  float t[kTH * kTS];
+  float hs[kTH * kHS];
+};
+
+template <typename TP, typename TM>
+__global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict__ pred, const TM* __restrict__ mask, float mscale, int H,
+                                                            int W, int Hm, int Wm, float focal_alpha, float focal_gamma,
+                                                            float* __restrict__ t_save, float* __restrict__ w_save,
+                                                            double* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SegSmem& sm = *reinterpret_cast<SegSmem*>(smem_raw);
+  __shared__ double scratch[kNP * 32];
+  const int tiles_x = (W + kT - 1) / kT, tiles_y = (H + kT - 1) / kT;
+  const int n = blockIdx.x / (tiles_x * tiles_y);
+  const int tile = blockIdx.x % (tiles_x * tiles_y);
+  const int ty0 = (tile / tiles_x) * kT, tx0 = (tile % tiles_x) * kT;
+  const bool same = (Hm == H && Wm == W);
+  const float sh = (float)Hm / (float)H, sw = (float)Wm / (float)W;
+  const TM* mbase = mask + (long long)n * Hm * Wm;
+
+  // 1. target tile with halo (zero outside the image: avg_pool2d zero padding, count_include_pad)
+  for (int i = threadIdx.x; i < kTH * kTH; i += blockDim.x) {
+    const int hy = i / kTH, hx = i % kTH;
+    const int gy = ty0 + hy - kHalo, gx = tx0 + hx - kHalo;
+    float v = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      if (same) {
+        v = to_f<TM>(__ldg(mbase + (long long)gy * Wm + gx)) * mscale;
+      } else {
+        int y0, y1, x0, x1;
+        float ly0, ly1, lx0, lx1;
+        src_index(sh, gy, Hm, y0, y1, ly0, ly1);
+        src_index(sw, gx, Wm, x0, x1, lx0, lx1);
+        const TM* r0 = mbase + (long long)y0 * Wm;
+        const TM* r1 = mbase + (long long)y1 * Wm;
+        v = (ly0 * (lx0 * to_f<TM>(__ldg(r0 + x0)) + lx1 * to_f<TM>(__ldg(r0 + x1))) +
+             ly1 * (lx0 * to_f<TM>(__ldg(r1 + x0)) + lx1 * to_f<TM>(__ldg(r1 + x1)))) * mscale;
+      }
+    }
+    sm.t[hy * kTS + hx] = v;
+  }
+  __syncthreads();
+
+  // 2. horizontal 31-sums: item = (segment of 16 columns, halo row)
+  for (int it = threadIdx.x; it < 4 * kTH; it += blockDim.x) {
+    const int hy = it % kTH, x0 = (it / kTH) * 16;
+    const float* row = sm.t + hy * kTS;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 31; ++d) s += row[x0 + d];
+    sm.hs[hy * kHS + x0] = s;
+#pragma unroll
+    for (int x = 1; x < 16; ++x) {
+      s += row[x0 + x + 30] - row[x0 + x - 1];
+      sm.hs[hy * kHS + x0 + x] = s;
+    }
+  }
+  __syncthreads();
+
+  // 3. vertical 31-sums + per-pixel terms: thread = (column, segment of 16 rows)
+  double acc[kNP];
+#pragma unroll
+  for (int k = 0; k < kNP; ++k) acc[k] = 0.0;
+  {
+    const int x = threadIdx.x & 63, y0 = (threadIdx.x >> 6) * 16;
+    const int gx = tx0 + x;
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 31; ++d) s += sm.hs[(y0 + d) * kHS + x];
+    float f[kNP];
+#pragma unroll
+    for (int k = 0; k < kNP; ++k) f[k] = 0.f;
+    for (int y = 0; y < 16; ++y) {
+      if (y > 0) s += sm.hs[(y0 + y + 30) * kHS + x] - sm.hs[(y0 + y - 1) * kHS + x];
+      const int gy = ty0 + y0 + y;
+      if (gy < H && gx < W) {
+        const float t = sm.t[(y0 + y + kHalo) * kTS + x + kHalo];
+        const float wgt = 1.f + 5.f * fabsf(s * (1.f / 961.f) - t);
+        const long long o = ((long long)n * H + gy) * W + gx;
+        const float z = to_f<TP>(__ldg(pred + o));
+        const float e = expf(-fabsf(z));
+        const float bce = (1.f - t) * z - (fminf(z, 0.f) - log1pf(e));
+        const float p = z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+        f[0] += wgt;
+        f[1] = fmaf(wgt, bce, f[1]);
+        f[2] = fmaf(p * t, wgt, f[2]);
+        f[3] = fmaf(p + t, wgt, f[3]);
+        f[4] = fmaf(p, t, f[4]);
+        f[5] += p;
+        f[6] += t;
+        const float pt = p * t + (1.f - p) * (1.f - t);
+        const float at = focal_alpha * t + (1.f - focal_alpha) * (1.f - t);
+        f[7] = fmaf(at * __powf(fmaxf(1.f - pt, 0.f), focal_gamma), bce, f[7]);
+        if (t_save) { t_save[o] = t; w_save[o] = wgt; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kNP; ++k) acc[k] = (double)f[k];
+  }
+  block_sum<kNP>(acc, scratch);
+  if (threadIdx.x == 0) {
+    double* o = part + (long long)blockIdx.x * kNP;
+#pragma unroll
+    for (int k = 0; k < kNP; ++k) o[k] = acc[k];
+  }
+}
+
+// per_sample[n][8] = tile sums in fixed order; out8 = {loss, dice, focal, mean wbce, mean wiou, 0,0,0}
+__global__ void __launch_bounds__(256) seg_loss_finalize_kernel(const double* __restrict__ part, int N, int tiles, int HW, float w1,
+                                                                float w2, float dice_smooth, float* __restrict__ per_sample,
+                                                                float* __restrict__ out8) {
+  __shared__ double scratch[5 * 32];
+  double v[5] = {0, 0, 0, 0, 0};
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    double s[kNP];
+    for (int k = 0; k < kNP; ++k) s[k] = 0.0;
+    for (int t = 0; t < tiles; ++t)
+      for (int k = 0; k < kNP; ++k) s[k] += part[((long long)n * tiles + t) * kNP + k];
+    for (int k = 0; k < kNP; ++k) per_sample[(long long)n * kNP + k] = (float)s[k];
+    const double wbce = s[1] / s[0];
+    const double inter = s[2], uni = s[3] - s[2];
+    const double wiou = 1.0 - (inter + 1e-6) / (uni + 1e-6);
+    v[0] += (double)w1 * wbce + (double)w2 * wiou;
+    v[1] += 1.0 - (2.0 * s[4] + dice_smooth) / (s[5] + s[6] + dice_smooth);
+    v[2] += s[7];
+    v[3] += wbce;
+    v[4] += wiou;
+  }
+  block_sum<5>(v, scratch);
+  if (threadIdx.x == 0) {
+    out8[0] = (float)(v[0] / N);
+    out8[1] = (float)(v[1] / N);
+    out8[2] = (float)(v[2] / ((double)N * HW));
+    out8[3] = (float)(v[3] / N);
+    out8[4] = (float)(v[4] / N);
+    out8[5] = out8[6] = out8[7] = 0.f;
+  }
+}
+
+// d loss / d pred, elementwise (4 pixels per thread).
+template <typename TP, typename TG>
+__global__ void __launch_bounds__(256) seg_loss_bwd_kernel(const TP* __restrict__ pred, const float* __restrict__ t_save,
+                                                           const float* __restrict__ w_save, const float* __restrict__ per_sample,
+                                                           int N, long long HW, float w1, float w2, const float* __restrict__ g_loss,
+                                                           TG* __restrict__ g_pred) {
+  const long long total = (long long)N * HW;
+  const float g = g_loss[0] / (float)N;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(o / HW);
+    const float* s = per_sample + (long long)n * kNP;
+    const float sw = s[0], I = s[2] + 1e-6f, U = s[3] - s[2] + 1e-6f;
+    const float z = to_f<TP>(pred[o]), t = t_save[o], w = w_save[o];
+    const float e = expf(-fabsf(z));
+    const float p = z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    const float dwbce = w * (p - t) / sw;
+    const float dratio = (t * w * U - I * w * (1.f - t)) / (U * U);   // d (I/U) / d p
+    g_pred[o] = from_f<TG>(g * (w1 * dwbce - w2 * dratio * p * (1.f - p)));
+  }
+}
+
+template <typename TP, typename TM>
+static int launch_tiles(const void* pred, const void* mask, float mscale, int N, int H, int W, int Hm, int Wm, float fa, float fg_,
+                        float* t_save, float* w_save, double* part, cudaStream_t st) {
+  const int tiles = ceil_div(H, kT) * ceil_div(W, kT);
+  auto k = seg_loss_tile_kernel<TP, TM>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem));
+  if (e != cudaSuccess) {
+    set_error("seg_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return COR_ECUDA;
+  }
+  k<<<N * tiles, 256, sizeof(SegSmem), st>>>((const TP*)pred, (const TM*)mask, mscale, H, W, Hm, Wm, fa, fg_, t_save, w_save, part);
+  return check_launch("seg_loss_tile_kernel");
+}
+
+}  // namespace cor
+
+using namespace cor;
+
+extern "C" size_t cor_seg_loss_work_bytes(int N, int H, int W) {
+  return (size_t)N * ceil_div(H, kT) * ceil_div(W, kT) * kNP * sizeof(double);
+}
+
+extern "C" int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* mask, int mask_dtype, float mask_scale, int N,
+                                int H, int W, int Hm, int Wm, float w1, float w2, float focal_alpha, float focal_gamma,
+                                float dice_smooth, float* out8, float* per_sample, float* t_save, float* w_save, void* work,
+                                cor_stream_t stream) {
+  COR_REQUIRE(pred && mask && out8 && per_sample && work, "cor_seg_loss_fwd: null pointer");
+  COR_REQUIRE(N > 0 && H > 0 && W > 0 && Hm > 0 && Wm > 0, "cor_seg_loss_fwd: bad shape");
+  COR_REQUIRE((t_save == nullptr) == (w_save == nullptr), "cor_seg_loss_fwd: t_save and w_save go together");
+  cudaStream_t st = as_stream(stream);
+  double* part = reinterpret_cast<double*>(work);
+  int rc = COR_EINVAL;
+#define COR_SEG(TP, TM) rc = launch_tiles<TP, TM>(pred, mask, mask_scale, N, H, W, Hm, Wm, focal_alpha, focal_gamma, t_save, w_save, part, st)
+  if (pred_dtype == COR_F32 && mask_dtype == COR_F32) COR_SEG(float, float);
+  else if (pred_dtype == COR_BF16 && mask_dtype == COR_F32) COR_SEG(bf16, float);
+  else if (pred_dtype == COR_F32 && mask_dtype == COR_U8) COR_SEG(float, uint8_t);
+  else if (pred_dtype == COR_BF16 && mask_dtype == COR_U8) COR_SEG(bf16, uint8_t);
+  else if (pred_dtype == COR_F32 && mask_dtype == COR_BF16) COR_SEG(float, bf16);
+  else if (pred_dtype == COR_BF16 && mask_dtype == COR_BF16) COR_SEG(bf16, bf16);
+  else COR_REQUIRE(false, "cor_seg_loss_fwd: unsupported dtypes pred=%d mask=%d", pred_dtype, mask_dtype);
+#undef COR_SEG
+  if (rc) return rc;
+  const int tiles = ceil_div(H, kT) * ceil_div(W, kT);
+  seg_loss_finalize_kernel<<<1, 256, 0, st>>>(part, N, tiles, H * W, w1, w2, dice_smooth, per_sample, out8);
+  return check_launch("seg_loss_finalize_kernel");
+}
+
+extern "C" int cor_seg_loss_bwd(const void* pred, int pred_dtype, const float* t_save, const float* w_save,
+                                const float* per_sample, int N, int H, int W, float w1, float w2, const float* g_loss,
+                                void* g_pred, int g_dtype, cor_stream_t stream) {
+  COR_REQUIRE(pred && t_save && w_save && per_sample && g_loss && g_pred, "cor_seg_loss_bwd: null pointer");
+  const long long HW = (long long)H * W;
+  const int blocks = (int)min((long long)sm_count() * 8, (N * HW + 255) / 256);
+  cudaStream_t st = as_stream(stream);
+#define COR_SEGB(TP, TG) seg_loss_bwd_kernel<TP, TG><<<blocks, 256, 0, st>>>((const TP*)pred, t_save, w_save, per_sample, N, HW, w1, w2, g_loss, (TG*)g_pred)
+  if (pred_dtype == COR_F32 && g_dtype == COR_F32) COR_SEGB(float, float);
+  else if (pred_dtype == COR_BF16 && g_dtype == COR_BF16) COR_SEGB(bf16, bf16);
+  else if (pred_dtype == COR_BF16 && g_dtype == COR_F32) COR_SEGB(bf16, float);
+  else COR_REQUIRE(false, "cor_seg_loss_bwd: unsupported dtypes pred=%d grad=%d", pred_dtype, g_dtype);
+#undef COR_SEGB
+  return check_launch("seg_loss_bwd_kernel");
+}

