@@ -58,8 +58,9 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_mask_prep", i, p, i, f, i, i, i, i, i, i, p, p, ll, i, ll, p, p, p)
         _sig(lib, "cor_pool_stream_fwd", i, p, i, p, ll, i, i, i, i, i, p, p, p)
         _sig(lib, "cor_pool_umma_work_bytes", sz, i, i, i, i)
-        _sig(lib, "cor_pool_umma_fwd", i, p, p, i, i, i, i, p, p, p)
-        _sig(lib, "cor_rows_finalize", i, p, i, ll, p, i, f, i, i, i, i, p, f, p, p, p, p)
+        _sig(lib, "cor_pool_umma_ksplit", i, i, i, i)
+        _sig(lib, "cor_pool_umma_fwd", i, p, p, i, i, i, i, p, p)
+        _sig(lib, "cor_rows_finalize", i, p, i, ll, i, ll, p, i, f, i, i, i, i, p, f, p, p, p, p)
         _sig(lib, "cor_rows_finalize_bwd", i, p, p, p, p, i, f, i, i, i, i, i, f, p, p)
         _sig(lib, "cor_pool_bwd_feat", i, p, p, p, ll, i, i, i, i, i, p, i, p)
         _sig(lib, "cor_pool_bwd_maps", i, p, i, p, ll, p, p, p, i, i, i, i, p, p)

@@ -13,6 +13,8 @@ namespace cor {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> COR_ECUDA
 int sm_count();                       // cached multiprocessor count of the current device
+// lse[q] from `nparts` (max,sum) partials laid out [qtile][nparts][qt][2] (sim_stream.cu)
+int launch_lse_combine(const float* part, int Nq, int nparts, int qt, float* lse, cudaStream_t st);
 
 #define COR_REQUIRE(cond, ...)          \
   do {                                  \

@@ -150,7 +150,7 @@ static int launch_pool_stream(const TF* feat, const float* wts, long long ldw, i
 // ---- row epilogue: divide, group mean, L2-normalise ---------------------------------------------
 // grid = rows_out, block = 256, dynamic smem = C floats.
 __global__ void __launch_bounds__(256) rows_finalize_kernel(const float* __restrict__ sums, int rows_per_image, long long img_stride,
-                                                            const float* __restrict__ den, int den_stride, float eps, int C, int G,
+                                                            int nsplit, long long split_stride, const float* __restrict__ den, int den_stride, float eps, int C, int G,
                                                             int normalize, const float* __restrict__ all, float p_total,
                                                             float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
                                                             float* __restrict__ inv_norm) {
@@ -164,9 +164,13 @@ __global__ void __launch_bounds__(256) rows_finalize_kernel(const float* __restr
       const long long i = (long long)j * G + g;
       const long long img = i / rows_per_image;
       float d = den[i * den_stride];
-      float s = sums[img * img_stride + (i % rows_per_image) * C + c];
+      const long long so = img * img_stride + (i % rows_per_image) * C + c;
+      float s = sums[so];
+      for (int k = 1; k < nsplit; ++k) s += sums[so + k * split_stride];
       if (all) {
-        s = all[img * img_stride + c] - s;
+        float a = all[img * img_stride + c];
+        for (int k = 1; k < nsplit; ++k) a += all[img * img_stride + c + k * split_stride];
+        s = a - s;
         d = p_total - d;
       }
       acc += s / (d + eps);
@@ -352,9 +356,10 @@ extern "C" int cor_pool_stream_fwd(const void* feat, int feat_dtype, const float
   COR_REQUIRE(false, "cor_pool_stream_fwd: unsupported feature dtype %d", feat_dtype);
 }
 
-extern "C" int cor_rows_finalize(const float* sums, int rows_per_image, long long img_stride, const float* den, int den_stride,
-                                 float eps, int rows_in, int C, int G, int normalize, const float* all_sum, float p_total,
-                                 float* out_f32, void* out_bf16, float* inv_norm, cor_stream_t stream) {
+extern "C" int cor_rows_finalize(const float* sums, int rows_per_image, long long img_stride, int nsplit, long long split_stride,
+                                 const float* den, int den_stride, float eps, int rows_in, int C, int G, int normalize,
+                                 const float* all_sum, float p_total, float* out_f32, void* out_bf16, float* inv_norm,
+                                 cor_stream_t stream) {
   COR_REQUIRE(sums && den && out_f32, "cor_rows_finalize: null pointer");
   COR_REQUIRE(rows_in > 0 && C > 0 && G > 0 && rows_in % G == 0 && den_stride > 0, "cor_rows_finalize: bad shape rows=%d C=%d G=%d",
               rows_in, C, G);
@@ -362,7 +367,8 @@ extern "C" int cor_rows_finalize(const float* sums, int rows_per_image, long lon
   if (rows_per_image <= 0) { rows_per_image = rows_in; img_stride = (long long)rows_in * C; }
   COR_REQUIRE(img_stride >= (long long)rows_per_image * C, "cor_rows_finalize: img_stride too small");
   rows_finalize_kernel<<<rows_in / G, 256, C * sizeof(float), as_stream(stream)>>>(
-      sums, rows_per_image, img_stride, den, den_stride, eps, C, G, normalize, all_sum, p_total, out_f32, (bf16*)out_bf16, inv_norm);
+      sums, rows_per_image, img_stride, nsplit, split_stride, den, den_stride, eps, C, G, normalize, all_sum, p_total, out_f32,
+      (bf16*)out_bf16, inv_norm);
   return check_launch("rows_finalize_kernel");
 }
 

@@ -379,6 +379,13 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ S, 
 
 }  // namespace cor
 
+namespace cor {
+int launch_lse_combine(const float* part, int Nq, int nparts, int qt, float* lse, cudaStream_t st) {
+  sim_lse_combine_kernel<<<ceil_div(Nq, 128), 128, 0, st>>>(part, Nq, nparts, qt, lse);
+  return check_launch("sim_lse_combine_kernel");
+}
+}  // namespace cor
+
 using namespace cor;
 
 static int stream_region_ctas(int Nr) {
@@ -420,8 +427,7 @@ extern "C" int cor_sim_stream_fwd(const void* regions, const void* queries, int 
   sim_stream_kernel<<<dim3(ctas, qtiles), 256, smem, st>>>((const bf16*)regions, (const bf16*)queries, Nr, Nq, D, inv_tau, S, part);
   int rc = check_launch("sim_stream_kernel");
   if (rc || !lse) return rc;
-  sim_lse_combine_kernel<<<ceil_div(Nq, 128), 128, 0, st>>>(part, Nq, ctas, kQT, lse);
-  return check_launch("sim_lse_combine_kernel");
+  return launch_lse_combine(part, Nq, ctas, kQT, lse, st);
 }
 
 extern "C" int cor_infonce_fwd(const void* regions, const void* queries, const long long* targets, const float* lse, int Nr,

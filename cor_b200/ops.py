@@ -26,7 +26,7 @@ _ll = C.c_longlong
 # launch counter: bench.py reports how many of OUR kernels ran inside the timed region
 LAUNCHES = {"count": 0}
 _KERNELS_PER_CALL = {
-    "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 2, "cor_rows_finalize": 1,
+    "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 1, "cor_rows_finalize": 1,
     "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
     "cor_fgbg_loss_bwd": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
     "cor_sim_umma_fwd": 2, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
@@ -159,17 +159,18 @@ class _RegionPoolFn(torch.autograd.Function):
             need_w32 = feat.requires_grad      # backward runs on the fp32 weights
             w32, stats = mask_prep(flat, (h, w), transform, want_f32=need_w32, bf16_out=w16, group=R, group_stride=Rp * P,
                                    mask_scale=mask_scale)
-            sums = torch.empty((B, Rp, Cc), dtype=torch.float32, device=dev)   # row R of each image = sum_p F
-            work = _work(lib.cor_pool_umma_work_bytes(B, Cc, P, Rp), dev)
-            _call("cor_pool_umma_fwd", dev, ptr(feat_c), ptr(w16), B, Cc, P, Rp, ptr(sums), ptr(work))
+            ks = lib.cor_pool_umma_ksplit(B, Cc, P)
+            part = torch.empty((ks, B, Rp, Cc), dtype=torch.float32, device=dev)   # split-K partials; row R = sum_p F
+            _call("cor_pool_umma_fwd", dev, ptr(feat_c), ptr(w16), B, Cc, P, Rp, ptr(part))
             den_col = 3
-            fg_sum = sums
-            _call("cor_rows_finalize", dev, ptr(sums), R, _ll(Rp * Cc), ptr(stats[:, den_col:]), 4, _f(eps), B * R, Cc, 1,
-                  int(normalize), None, _f(0.0), ptr(fg), ptr(fg16), ptr(inv_fg))
+            fg_sum = None
+            split = B * Rp * Cc
+            _call("cor_rows_finalize", dev, ptr(part), R, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, den_col:]), 4, _f(eps), B * R, Cc,
+                  1, int(normalize), None, _f(0.0), ptr(fg), ptr(fg16), ptr(inv_fg))
             if pair:
-                all_sum = sums[:, R, :]           # view: image b at b * Rp * C floats
-                _call("cor_rows_finalize", dev, ptr(sums), R, _ll(Rp * Cc), ptr(stats[:, den_col:]), 4, _f(eps), B * R, Cc, 1,
-                      int(normalize), ptr(all_sum), _f(float(P)), ptr(bg), None, ptr(inv_bg))
+                all_sum = part[0, :, R, :]        # view: image b at b * Rp * C floats, split k at k * split
+                _call("cor_rows_finalize", dev, ptr(part), R, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, den_col:]), 4, _f(eps), B * R,
+                      Cc, 1, int(normalize), ptr(all_sum), _f(float(P)), ptr(bg), None, ptr(inv_bg))
             bg_sum = None
         else:
             den_col = 2
@@ -178,13 +179,13 @@ class _RegionPoolFn(torch.autograd.Function):
             bg_sum = torch.empty((B, R, Cc), dtype=torch.float32, device=dev) if pair else None
             _call("cor_pool_stream_fwd", dev, ptr(feat_c), dtype_code(feat_c), ptr(w32), _ll(P), B, Cc, P, R, int(transform),
                   ptr(fg_sum), ptr(bg_sum))
-            _call("cor_rows_finalize", dev, ptr(fg_sum), 0, _ll(0), ptr(stats[:, den_col:]), 4, _f(eps), B * R, Cc, int(group),
+            _call("cor_rows_finalize", dev, ptr(fg_sum), 0, _ll(0), 1, _ll(0), ptr(stats[:, den_col:]), 4, _f(eps), B * R, Cc, int(group),
                   int(normalize), None, _f(0.0), ptr(fg), ptr(fg16), ptr(inv_fg))
             if pair:
                 # background denominators: P - den  (sum_p (1 - w))
                 den_bg = (float(P) - stats[:, den_col]).contiguous()
                 ctx.den_bg = den_bg
-                _call("cor_rows_finalize", dev, ptr(bg_sum), 0, _ll(0), ptr(den_bg), 1, _f(eps), B * R, Cc, int(group),
+                _call("cor_rows_finalize", dev, ptr(bg_sum), 0, _ll(0), 1, _ll(0), ptr(den_bg), 1, _f(eps), B * R, Cc, int(group),
                       int(normalize), None, _f(0.0), ptr(bg), None, ptr(inv_bg))
         ctx.cfg = (B, Cc, h, w, R, int(transform), bool(normalize), bool(pair), int(group), float(eps), den_col, use_umma,
                    feat_c.dtype, feat.dtype, tuple(masks.shape))

@@ -75,23 +75,27 @@ int cor_pool_stream_fwd(const void* feat, int feat_dtype, const float* wts, long
 
 /* Tensor-core (tcgen05 / TMEM, TMA-staged) variant for bf16 features and many masks:
  *   feat [B, C, P] bf16 (P % 64 == 0, C % 128 == 0), wts [B, Rp, P] bf16 with Rp % 16 == 0 and
- *   Rp <= 256; row Rp-1 may be all ones so that fg_sum[:, Rp-1, :] is sum_p F (background by
- *   subtraction).  fg_sum [B, Rp, C] f32.  work: cor_pool_umma_work_bytes().                  */
-size_t cor_pool_umma_work_bytes(int B, int C, int P, int Rp);
+ *   16 <= Rp <= 256; one row of wts may be all ones so that its pooled sum is sum_p F (background
+ *   by subtraction).  Split-K over the mask pixels: writes ksplit = cor_pool_umma_ksplit(B,C,P)
+ *   fp32 partial tiles part [ksplit, B, Rp, C]; cor_rows_finalize sums them in fixed order.      */
+int cor_pool_umma_ksplit(int B, int C, int P);
+size_t cor_pool_umma_work_bytes(int B, int C, int P, int Rp);   /* bytes of `part` */
 int cor_pool_umma_fwd(const void* feat_bf16, const void* wts_bf16, int B, int C, int P, int Rp,
-                      float* fg_sum, void* work, cor_stream_t stream);
+                      float* part, cor_stream_t stream);
 
 /* Row epilogue: divide by the denominator, optional group mean, optional L2-normalise
  * (loss_func.py:51-53; mask_adapter.py:23, :77-79).  One row = one (image, mask).
- *   sums: row i lives at (i / rows_per_image) * img_stride + (i % rows_per_image) * C floats;
+ *   sums: row i lives at (i / rows_per_image) * img_stride + (i % rows_per_image) * C floats, and is
+ *         the fixed-order sum of nsplit partial copies split_stride floats apart (nsplit <= 1: none);
  *   den [rows_in] (stride den_stride floats); eps added to den;
  *   group G >= 1: output row j = mean of input rows j*G .. j*G+G-1 after division;
  *   out_f32 [rows_in/G, C] ; out_bf16 same shape or NULL ; inv_norm [rows_in/G] (1/max(|p|,1e-12)
  *   when normalize, else 1) saved for backward.  If all_sum != NULL the row is the BACKGROUND
- *   (all_sum[b] - sums[row]) / (p_total - den + eps), all_sum[b] at b * img_stride floats. */
-int cor_rows_finalize(const float* sums, int rows_per_image, long long img_stride, const float* den, int den_stride,
-                      float eps, int rows_in, int C, int G, int normalize, const float* all_sum, float p_total,
-                      float* out_f32, void* out_bf16, float* inv_norm, cor_stream_t stream);
+ *   (all_sum[b] - sums[row]) / (p_total - den + eps), all_sum[b] at b * img_stride floats (+ splits). */
+int cor_rows_finalize(const float* sums, int rows_per_image, long long img_stride, int nsplit, long long split_stride,
+                      const float* den, int den_stride, float eps, int rows_in, int C, int G, int normalize,
+                      const float* all_sum, float p_total, float* out_f32, void* out_bf16, float* inv_norm,
+                      cor_stream_t stream);
 
 /* Backward of cor_rows_finalize: g_out [rows_out, C] -> g_sums [rows_in, C], the gradient w.r.t. the
  * sum row the epilogue consumed (for bg_from_all rows: w.r.t. the background sum all - fg). */

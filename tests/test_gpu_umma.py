@@ -1,0 +1,135 @@
+"""GPU parity of the tcgen05 / TMEM / TMA kernels (pool_umma.cu, sim_umma.cu) against the CPU oracle and
+against the exact-fp32 streaming kernels.  Run with ``-m gpu`` on a B200."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def cu(x, dtype=None, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dev())
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.requires_grad_(grad)
+
+
+def close(a, b, rtol=1e-3, atol=1e-3):
+    a = a.detach().float().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    np.testing.assert_allclose(a.astype(np.float64), b.astype(np.float64), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 128, 16, 16), (3, 40, 256, 32, 32), (1, 100, 384, 64, 64), (2, 255, 128, 8, 8)])
+def test_pool_umma_vs_oracle_and_stream(shape):
+    """bf16 features, M masks: tensor-core pooling == oracle within the north-star tolerance and
+    == the fp32 streaming kernel fed the same bf16 features."""
+    from cor_b200 import ops, synth
+    from oracle import np_oracle as no
+    B, M, C, h, w = shape
+    d = synth.make_triplets(41 + M, B=B, M=M, C=C, h=h, w=w, H=4 * h, W=4 * w, hp=8, wp=8, degenerate=True)
+    emb16 = torch.from_numpy(d["emb"]).bfloat16()
+    masks = cu(d["masks"])
+    pu = ops.region_pool(emb16.to(dev()), masks, transform=ops.W_CLAMP, normalize=True, pair=True, engine="umma", want_bf16=True)
+    ps = ops.region_pool(emb16.to(dev()), masks, transform=ops.W_CLAMP, normalize=True, pair=True, engine="stream")
+    ref_fg = no.multi_mask_pool(emb16.float().numpy(), d["masks"])
+    ref_bg = no.multi_mask_pool(emb16.float().numpy(), d["masks"], background=True)
+    close(pu.fg, ref_fg, rtol=1e-3, atol=1e-3)
+    close(pu.bg, ref_bg, rtol=1e-3, atol=1e-3)
+    close(pu.fg, ps.fg, rtol=1e-3, atol=5e-4)
+    close(pu.bg, ps.bg, rtol=1e-3, atol=5e-4)
+    close(pu.fg_bf16.view_as(pu.fg), pu.fg, rtol=1e-2, atol=4e-3)
+    assert torch.equal(pu.stats[:, :2], ps.stats[:, :2])
+    # determinism: split-K partials are summed in fixed order
+    pu2 = ops.region_pool(emb16.to(dev()), masks, transform=ops.W_CLAMP, normalize=True, pair=True, engine="umma")
+    assert torch.equal(pu.fg, pu2.fg) and torch.equal(pu.bg, pu2.bg)
+
+
+def test_pool_umma_unnormalised_sums_hard_masks_exact_weights():
+    """Hard masks at 4x scale resample to {0,.25,.5,.75,1}: exact in bf16, so with bf16 features the
+    tensor-core sums equal the fp32 streaming sums up to accumulation order."""
+    from cor_b200 import ops, synth
+    d = synth.make_triplets(43, B=2, M=24, C=128, h=32, w=32, H=128, W=128, hp=8, wp=8, degenerate=False)
+    emb16 = torch.from_numpy(d["emb"]).bfloat16().to(dev())
+    a = ops.region_pool(emb16, cu(d["masks"]), transform=ops.W_CLAMP, normalize=False, engine="umma")
+    b = ops.region_pool(emb16, cu(d["masks"]), transform=ops.W_CLAMP, normalize=False, engine="stream")
+    close(a.fg, b.fg, rtol=2e-5, atol=2e-5)
+
+
+def test_pool_umma_backward_matches_stream():
+    from cor_b200 import ops, synth
+    d = synth.make_triplets(47, B=2, M=20, C=128, h=16, w=16, H=64, W=64, hp=8, wp=8, degenerate=False)
+    g = torch.randn(2, 20, 128, device=dev())
+    grads = []
+    for eng in ("umma", "stream"):
+        e = torch.from_numpy(d["emb"]).bfloat16().to(dev()).requires_grad_(True)
+        p = ops.region_pool(e, cu(d["masks"]), transform=ops.W_CLAMP, normalize=True, pair=True, engine=eng)
+        (p.fg * g).sum().backward(retain_graph=True)
+        (p.bg * g.flip(0)).sum().backward()
+        grads.append(e.grad.float())
+    close(grads[0], grads[1], rtol=2e-2, atol=2e-3)
+
+
+@pytest.mark.parametrize("shape", [(300, 20, 256), (4096, 256, 256), (1000, 130, 128), (257, 1, 64), (5000, 16, 256), (770, 300, 192)])
+def test_sim_umma_vs_oracle(shape):
+    from cor_b200 import ops, synth
+    from oracle import np_oracle as no
+    Nr, Nq, D = shape
+    g = synth.make_gallery(53 + Nq, Nr, Nq, D=D)
+    S = ops.similarity(cu(g["regions"]), cu(g["queries"]), engine="umma")
+    ref = no.region_query_similarity(g["regions"], g["queries"])
+    close(S, ref, rtol=1e-3, atol=2e-6)
+    Ss = ops.similarity(cu(g["regions"]), cu(g["queries"]), engine="stream")
+    close(S, Ss, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(300, 20, 256), (4096, 256, 256), (1000, 130, 128), (20000, 16, 256)])
+def test_infonce_umma(shape):
+    from cor_b200 import ops, synth
+    from oracle import np_oracle as no
+    Nr, Nq, D = shape
+    g = synth.make_gallery(59 + Nq, Nr, Nq, D=D)
+    t = (np.arange(Nq) * 13) % Nr
+    r, q = cu(g["regions"], grad=True), cu(g["queries"], grad=True)
+    loss = ops.infonce_loss(r, q, cu(t), tau=0.07, engine="umma")
+    close(loss, no.infonce_loss(g["regions"], g["queries"], t, 0.07), rtol=1e-3, atol=1e-5)
+    ls = ops.infonce_loss(cu(g["regions"]), cu(g["queries"]), cu(t), tau=0.07, engine="stream")
+    close(loss, ls, rtol=1e-5, atol=1e-6)
+    if D <= 256 and Nq <= 64:
+        loss.backward()
+        assert torch.isfinite(r.grad).all() and torch.isfinite(q.grad).all()
+
+
+@pytest.mark.parametrize("k", [1, 10, 50])
+def test_topk_umma_identical_indices(k):
+    """BASELINE config 3: 256 queries x 4096 regions; indices identical to the oracle's total order."""
+    from cor_b200 import region, synth
+    from oracle import np_oracle as no
+    g = synth.make_gallery(61, 4096, 256, D=256, duplicate=True)
+    idx, sc = region.topk_regions(cu(g["regions"]), cu(g["queries"]), k, engine="umma")
+    ridx, rsc = no.topk_retrieve(g["regions"], g["queries"], k)
+    assert (idx.cpu().numpy() == ridx).all()
+    np.testing.assert_array_equal(sc.cpu().numpy(), rsc)
+
+
+def test_region_step_auto_engines_vs_cpu_port():
+    """The fused step with the tensor-core pooling engine (bf16 features) against the ATen port."""
+    from cor_b200 import region, synth
+    from oracle import aten_port as ap
+    d = synth.make_triplets(67, B=2, M=16, C=128, h=16, w=16, H=128, W=128, hp=32, wp=32, degenerate=False)
+    emb16 = torch.from_numpy(d["emb"]).bfloat16()
+    p, c = cu(d["pred"], grad=True), cu(d["comb"], grad=True)
+    e = emb16.to(dev()).requires_grad_(True)
+    out = region.region_step(p, e, c, cu(d["masks"]), tau=0.07, gather=False, pool_engine="umma", sim_engine="stream")
+    pc, cc = (torch.from_numpy(d[k]).requires_grad_(True) for k in ("pred", "comb"))
+    ec = emb16.float().requires_grad_(True)
+    ref, _ = ap.region_step_loss(pc, ec, cc, torch.from_numpy(d["masks"]), tau=0.07)
+    close(out.loss, ref.item(), rtol=2e-3, atol=2e-3)
+    out.loss.backward()
+    ref.backward()
+    close(c.grad, cc.grad.numpy(), rtol=2e-2, atol=2e-3)
+    close(p.grad, pc.grad.numpy(), rtol=2e-3, atol=1e-7)
