@@ -29,6 +29,9 @@ import torch  # noqa: E402
 METRIC = "region_scored_triplets_per_sec"
 UNIT = "triplets/s"
 CFG = dict(B=16, M=64, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, tau=0.07)
+# dram__bytes_read.sum + dram__bytes_write.sum per mask_prep_kernel launch from the committed ncu --set full capture
+# (profiles/): filled in from the capture of the SAME configuration, else null.
+TRAFFIC_NCU = {"f32": None, "u8": None}
 
 
 def peaks():
@@ -49,25 +52,25 @@ def device_inputs(dev, seed, cfg, mask_dtype):
     comb = torch.nn.functional.normalize(torch.randn(B, 1, cfg["C"], device=dev, generator=g), dim=-1)
     pred = torch.nn.functional.avg_pool2d(2 * torch.randn(B, 1, cfg["hp"] + 4, cfg["wp"] + 4, device=dev, generator=g), 5, 1) * 5
     pred = pred.bfloat16()
-    masks = torch.zeros(B, M, H, W, device=dev, dtype=torch.float32)
-    yy = torch.arange(H, device=dev, dtype=torch.float32)[:, None]
-    xx = torch.arange(W, device=dev, dtype=torch.float32)[None, :]
-    r = torch.rand(B, M, 8, device=dev, generator=g).cpu().numpy()
-    for b in range(B):
-        for m in range(M):
-            i = b * M + m
-            if i % 32 == 31:
-                continue
-            if i % 256 == 129:
-                masks[b, m] = 1.0
-                continue
-            side = float(np.sqrt(0.005 + 0.295 * r[b, m, 0]))
-            rh, rw = max(2, int(H * side * (0.4 + 0.6 * r[b, m, 1]))), max(2, int(W * side * (0.4 + 0.6 * r[b, m, 2])))
-            y0, x0 = int(r[b, m, 3] * (H - rh)), int(r[b, m, 4] * (W - rw))
-            masks[b, m, y0:y0 + rh, x0:x0 + rw] = 1.0
-            cy, cx = (0.2 + 0.6 * r[b, m, 5]) * H, (0.2 + 0.6 * r[b, m, 6]) * W
-            ry, rx = max(2.0, H * side * 0.4), max(2.0, W * side * 0.4)
-            masks[b, m][((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0] = 1.0
+    masks = torch.empty(B, M, H, W, device=dev, dtype=torch.float32)
+    yy = torch.arange(H, device=dev, dtype=torch.float32).view(1, H, 1)
+    xx = torch.arange(W, device=dev, dtype=torch.float32).view(1, 1, W)
+    r = torch.rand(B, M, 8, device=dev, generator=g)
+    idx = torch.arange(B * M, device=dev).view(B, M)
+    side = torch.sqrt(0.005 + 0.295 * r[..., 0])
+    rh = torch.clamp((H * side * (0.4 + 0.6 * r[..., 1])).floor(), min=2)
+    rw = torch.clamp((W * side * (0.4 + 0.6 * r[..., 2])).floor(), min=2)
+    y0, x0 = (r[..., 3] * (H - rh)).floor(), (r[..., 4] * (W - rw)).floor()
+    cy, cx = (0.2 + 0.6 * r[..., 5]) * H, (0.2 + 0.6 * r[..., 6]) * W
+    ry, rx = torch.clamp(H * side * 0.4, min=2.0), torch.clamp(W * side * 0.4, min=2.0)
+    v = lambda t, b_: t[b_].view(M, 1, 1)
+    for b_ in range(B):       # one image at a time: [M,H,W] temporaries stay at 256 MB
+        rect = (yy >= v(y0, b_)) & (yy < v(y0 + rh, b_)) & (xx >= v(x0, b_)) & (xx < v(x0 + rw, b_))
+        ell = ((yy - v(cy, b_)) / v(ry, b_)) ** 2 + ((xx - v(cx, b_)) / v(rx, b_)) ** 2 <= 1.0
+        m = (rect | ell).float()
+        m[idx[b_] % 32 == 31] = 0.0
+        m[idx[b_] % 256 == 129] = 1.0
+        masks[b_] = m
     if mask_dtype == "u8":
         masks = (masks * 255).to(torch.uint8)
     return {"pred": pred, "emb": emb, "comb": comb, "masks": masks}
@@ -192,6 +195,8 @@ def main():
     ap_.add_argument("--cpu-triplets", type=int, default=1, help="triplets per CPU-baseline step (bounded sample)")
     ap_.add_argument("--cpu-iters", type=int, default=3)
     ap_.add_argument("--no-cpu-baseline", action="store_true")
+    ap_.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap_.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     ap_.add_argument("--pool-engine", default="auto")
     ap_.add_argument("--sim-engine", default="auto")
     args = ap_.parse_args()
@@ -215,14 +220,9 @@ def main():
 
     inp = device_inputs(dev, 1234 + rank, cfg, args.mask_dtype)
     kw = dict(tau=cfg["tau"], gather=world > 1, pool_engine=args.pool_engine, sim_engine=args.sim_engine)
-
-    def step_device():
-        p = inp["pred"].detach().requires_grad_(True)
-        c = inp["comb"].detach().requires_grad_(True)
-        e = inp["emb"].detach().requires_grad_(True)
-        out = region.region_step(p, e, c, inp["masks"], **kw)
-        out.loss.backward()
-        return out.loss
+    bufs = region.StepBuffers(cfg["B"], cfg["M"], cfg["C"], cfg["h"], cfg["w"], cfg["H"], cfg["W"], cfg["hp"], cfg["wp"], device=dev,
+                              mask_dtype=inp["masks"].dtype)
+    bufs.load(inp)
 
     def barrier():
         if world > 1:
@@ -235,46 +235,79 @@ def main():
         host_small = {k: v[:args.cpu_triplets].cpu() for k, v in inp.items()}
         cpu, _ = cpu_baseline(host_small, cfg, args.cpu_triplets, args.cpu_iters)
 
-    # ---- device-resident throughput
+    # ---- warm-up (eager), then capture fwd+bwd of the step into one CUDA graph
     for _ in range(args.warmup):
-        step_device()
+        bufs._step(True, True, kw)
     barrier()
-    ops.TIMING["events"] = {}
+    graphed = False
+    if not args.no_graph:
+        try:
+            bufs.capture(backward=True, emb_grad=True, warmup=1, **kw)
+            graphed = True
+        except Exception as e:  # e.g. a collective that cannot be captured: stay eager, say so
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            bufs.graph = None
+            torch.cuda.synchronize()
+    step = bufs.replay if graphed else (lambda: bufs._step(True, True, kw)[0])
+    for _ in range(2):
+        step()
+    barrier()
+
+    # ---- device-resident throughput: EXACTLY K steps between events, max over ranks
     n0 = ops.LAUNCHES["count"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()     # ncu --profile-from-start off captures only the timed region
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(args.steps):
-            loss = step_device()
+            loss = step()
         e1.record()
         barrier()
+    torch.cuda.profiler.stop()
     launches = ops.LAUNCHES["count"] - n0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    ms_step = float(ms) / args.steps
+    value = cfg["B"] * world / (ms_step * 1e-3)
+
+    # ---- per-kernel durations: the same K steps once more, eager, with CUDA events around every C-ABI call
+    ops.TIMING["events"] = {}
+    for _ in range(args.steps):
+        bufs._step(True, True, kw)
+    barrier()
     events, ops.TIMING["events"] = ops.TIMING["events"], None
     per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in events.items()}   # ms per step
     calls = {k: len(v) // args.steps for k, v in events.items()}
-    ms_step = ms_total / args.steps
-    value = cfg["B"] * world / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel (mask_prep: one pass over the full-resolution masks)
     esz = 4 if args.mask_dtype == "f32" else 1
     n_masks, P = cfg["B"] * cfg["M"], cfg["h"] * cfg["w"]
-    w32_written = True     # backward needs the fp32 weights (emb_grad)
-    prep_bytes = n_masks * cfg["H"] * cfg["W"] * esz + n_masks * P * (2 + (4 if w32_written else 0)) + n_masks * 16
+    prep_bytes = n_masks * cfg["H"] * cfg["W"] * esz + n_masks * P * (2 + 4) + n_masks * 16   # masks in; bf16 + f32 weights, stats out
     dom = max(per_kernel, key=per_kernel.get)
     prep_ms = per_kernel.get("cor_mask_prep", 0.0) / max(1, calls.get("cor_mask_prep", 1))
     achieved = prep_bytes / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0
     roofline = {"kernel": "mask_prep_kernel (cor_mask_prep)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                "algorithmic_bytes_per_launch": prep_bytes, "ms_per_launch": prep_ms, "share_of_step": per_kernel.get("cor_mask_prep", 0.0) / ms_step,
-                "dominant_by_events": dom}
+                "frac": achieved / hbm_peak, "traffic": TRAFFIC_NCU.get(args.mask_dtype), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                "algorithmic_bytes_per_launch": prep_bytes, "ms_per_launch": prep_ms,
+                "share_of_kernel_time": per_kernel.get("cor_mask_prep", 0.0) / max(1e-9, sum(per_kernel.values())),
+                "dominant_by_events": dom, "timed": "CUDA events around the C-ABI call, eager pass over the same K steps"}
+    pool_ms = per_kernel.get("cor_pool_umma_fwd", 0.0)
+    pool_bytes = cfg["B"] * (cfg["C"] * P * 2 + (cfg["M"] + 16) // 16 * 16 * P * 2)
+    secondary = {"pool_umma_kernel": {"bound": "hbm", "algorithmic_bytes": pool_bytes, "ms": pool_ms,
+                                      "achieved_gbs": pool_bytes / (pool_ms * 1e-3) / 1e9 if pool_ms > 0 else None,
+                                      "flops": 2.0 * cfg["B"] * cfg["M"] * P * cfg["C"]}}
+
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": ms_step, "e2e": None,
+                              "roofline": roofline, "kernel_ms_per_step": per_kernel, "gpu_launches": launches, "graphed": graphed,
+                              "note": "profiling run"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the public API with host buffers (H2D of the step's inputs + D2H of the loss)
-    bufs = region.StepBuffers(cfg["B"], cfg["M"], cfg["C"], cfg["h"], cfg["w"], cfg["H"], cfg["W"], cfg["hp"], cfg["wp"], device=dev,
-                              mask_dtype=inp["masks"].dtype)
     host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in inp.items()}
     for k in host:
         host[k].copy_(inp[k])
@@ -302,9 +335,9 @@ def main():
                 "data": "synthetic", "config": workload_config(cfg, args), "clocks": clk.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": bufs.h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": float(e2e_ms), "steps": e2e_steps},
-                "gpu_launches": launches, "roofline": roofline,
+                "gpu_launches": launches, "graphed": graphed, "roofline": roofline, "secondary_kernels": secondary,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
-                "loss": float(loss)}
+                "loss": float(loss.detach())}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
