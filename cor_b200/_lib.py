@@ -63,6 +63,8 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_rows_finalize", i, p, i, ll, i, ll, p, i, f, i, i, i, i, p, f, p, p, p, p)
         _sig(lib, "cor_rows_finalize_bwd", i, p, p, p, p, i, f, i, i, i, i, i, f, p, p)
         _sig(lib, "cor_pool_bwd_feat", i, p, p, p, ll, i, i, i, i, i, p, i, p)
+        _sig(lib, "cor_pool_bwd_umma_ok", i, i, i, i, i, i)
+        _sig(lib, "cor_pool_bwd_umma", i, p, p, p, ll, i, i, i, i, i, p, i, p)
         _sig(lib, "cor_pool_bwd_maps", i, p, i, p, ll, p, p, p, i, i, i, i, p, p)
         _sig(lib, "cor_fgbg_aux_floats", sz, i, i)
         _sig(lib, "cor_fgbg_loss_fwd", i, p, p, ll, p, ll, p, ll, i, i, i, p, p, p)

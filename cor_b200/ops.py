@@ -27,7 +27,7 @@ _ll = C.c_longlong
 LAUNCHES = {"count": 0}
 _KERNELS_PER_CALL = {
     "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 1, "cor_rows_finalize": 1,
-    "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
+    "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_umma": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
     "cor_fgbg_loss_bwd": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
     "cor_sim_umma_fwd": 2, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
     "cor_val_post": 3,
@@ -190,6 +190,7 @@ class _RegionPoolFn(torch.autograd.Function):
         ctx.cfg = (B, Cc, h, w, R, int(transform), bool(normalize), bool(pair), int(group), float(eps), den_col, use_umma,
                    feat_c.dtype, feat.dtype, tuple(masks.shape))
         ctx.feat_needs = feat.requires_grad
+        ctx.engine = engine
         ctx.maps_need = masks.requires_grad
         saved_feat = feat_c if masks.requires_grad else None
         ctx.save_for_backward(w32 if need_w32 else None, stats, fg, bg, inv_fg, inv_bg, saved_feat,
@@ -229,8 +230,9 @@ class _RegionPoolFn(torch.autograd.Function):
                       ptr(ctx.den_bg), 1, _f(eps), B * R, Cc, group, int(normalize), 0, _f(0.0), ptr(gs_bg))
         if ctx.feat_needs:
             g_feat_c = torch.empty((B, Cc, h, w), dtype=feat_dtype, device=dev)
-            _call("cor_pool_bwd_feat", dev, ptr(gs_fg), ptr(gs_bg), ptr(w32), _ll(P), B, Cc, P, R, transform, ptr(g_feat_c),
-                  L._DTYPES[feat_dtype])
+            tc = ctx.engine != "stream" and L.load().cor_pool_bwd_umma_ok(B, Cc, P, R, int(gs_bg is not None))
+            _call("cor_pool_bwd_umma" if tc else "cor_pool_bwd_feat", dev, ptr(gs_fg), ptr(gs_bg), ptr(w32), _ll(P), B, Cc, P, R,
+                  transform, ptr(g_feat_c), L._DTYPES[feat_dtype])
             g_feat = g_feat_c if feat_in_dtype == feat_dtype else g_feat_c.to(feat_in_dtype)
         if ctx.maps_need:
             if transform != W_SIGMOID:

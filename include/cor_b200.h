@@ -108,6 +108,13 @@ int cor_rows_finalize_bwd(const float* g_out, const float* out_f32, const float*
 int cor_pool_bwd_feat(const float* g_fg, const float* g_bg, const float* wts, long long ldw, int B, int C, int P,
                       int R, int transform, void* g_feat, int feat_dtype, cor_stream_t stream);
 
+/* Same contraction on tcgen05 tensor cores (bf16 operands built in shared memory from the fp32 inputs,
+ * fp32 accumulate in TMEM); write-bound.  cor_pool_bwd_umma_ok() says whether a shape is served
+ * (C % 128 == 0, P % 256 == 0, R (+1 with g_bg) <= 256); otherwise use cor_pool_bwd_feat. */
+int cor_pool_bwd_umma_ok(int B, int C, int P, int R, int has_bg);
+int cor_pool_bwd_umma(const float* g_fg, const float* g_bg, const float* wts, long long ldw, int B, int C, int P,
+                      int R, int transform, void* g_feat, int feat_dtype, cor_stream_t stream);
+
 /* Backward w.r.t. the (sigmoid) maps of the MaskAdapter tail (mask_adapter.py:71-79):
  *   g_x[b,r,p] = s(1-s)/den_r * ( sum_c g_sum... ) -- see DESIGN.md; g_pooled is d/d(pooled row). */
 int cor_pool_bwd_maps(const void* feat, int feat_dtype, const float* maps, long long ldw, const float* g_pooled,

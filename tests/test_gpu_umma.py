@@ -133,3 +133,26 @@ def test_region_step_auto_engines_vs_cpu_port():
     ref.backward()
     close(c.grad, cc.grad.numpy(), rtol=2e-2, atol=2e-3)
     close(p.grad, pc.grad.numpy(), rtol=2e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 256, 64, 64, torch.bfloat16, True), (1, 255, 128, 16, 16, torch.float32, True),
+                                 (2, 7, 128, 32, 32, torch.float32, False), (1, 100, 384, 32, 16, torch.bfloat16, True)])
+def test_pool_bwd_umma_vs_cuda_core(cfg):
+    """Tensor-core backward of the pooling contraction vs the fp32 CUDA-core kernel (same saved weights)."""
+    from cor_b200 import ops, synth
+    B, M, C, h, w, dt, pair = cfg
+    d = synth.make_triplets(71 + M, B=B, M=M, C=C, h=h, w=w, H=2 * h, W=2 * w, hp=8, wp=8, soft=True, degenerate=False)
+    g1 = torch.randn(B, M, C, device=dev())
+    g2 = torch.randn(B, M, C, device=dev())
+    grads = []
+    for eng in ("auto", "stream"):
+        e = torch.from_numpy(d["emb"]).to(dt).to(dev()).requires_grad_(True)
+        p = ops.region_pool(e, cu(d["masks"]), transform=ops.W_CLAMP, normalize=False, pair=pair, engine=eng)
+        loss = (p.fg * g1).sum() + ((p.bg * g2).sum() if pair else 0.0)
+        loss.backward()
+        grads.append(e.grad.float())
+    scale = float(grads[1].abs().max())
+    close(grads[0], grads[1], rtol=2e-2, atol=1e-2 * scale)
+    # relative Frobenius error: bf16 operand rounding only
+    err = float((grads[0] - grads[1]).norm() / grads[1].norm())
+    assert err < 6e-3, err
