@@ -34,6 +34,15 @@ CFG = dict(B=16, M=64, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, tau=0.
 TRAFFIC_NCU = {"f32": None, "u8": None}
 
 
+_T0 = time.perf_counter()
+
+
+def trace(msg):
+    """Stage markers on stderr (COR_BENCH_TRACE=1): locate a stall without a debugger."""
+    if os.environ.get("COR_BENCH_TRACE"):
+        print(f"[bench +{time.perf_counter() - _T0:7.2f}s rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -215,10 +224,14 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
+    trace("init done")
     hbm_peak, tc_peak, peak_kind = peaks()
 
     inp = device_inputs(dev, 1234 + rank, cfg, args.mask_dtype)
+    trace("inputs ready")
     kw = dict(tau=cfg["tau"], gather=world > 1, pool_engine=args.pool_engine, sim_engine=args.sim_engine)
     bufs = region.StepBuffers(cfg["B"], cfg["M"], cfg["C"], cfg["h"], cfg["w"], cfg["H"], cfg["W"], cfg["hp"], cfg["wp"], device=dev,
                               mask_dtype=inp["masks"].dtype)
@@ -235,10 +248,12 @@ def main():
         host_small = {k: v[:args.cpu_triplets].cpu() for k, v in inp.items()}
         cpu, _ = cpu_baseline(host_small, cfg, args.cpu_triplets, args.cpu_iters)
 
+    trace("eager warm-up")
     # ---- warm-up (eager), then capture fwd+bwd of the step into one CUDA graph
     for _ in range(args.warmup):
         bufs._step(True, True, kw)
     barrier()
+    trace("capture")
     graphed = False
     if not args.no_graph:
         try:
@@ -253,6 +268,7 @@ def main():
         step()
     barrier()
 
+    trace("timed loop")
     # ---- device-resident throughput: EXACTLY K steps between events, max over ranks
     n0 = ops.LAUNCHES["count"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -271,6 +287,7 @@ def main():
     ms_step = float(ms) / args.steps
     value = cfg["B"] * world / (ms_step * 1e-3)
 
+    trace("events pass")
     # ---- per-kernel durations: the same K steps once more, eager, with CUDA events around every C-ABI call
     ops.TIMING["events"] = {}
     for _ in range(args.steps):
@@ -302,11 +319,14 @@ def main():
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": ms_step, "e2e": None,
                               "roofline": roofline, "kernel_ms_per_step": per_kernel, "gpu_launches": launches, "graphed": graphed,
-                              "note": "profiling run"}))
+                              "note": "profiling run"}), flush=True)
         if world > 1:
-            dist.destroy_process_group()
+            bufs.graph = None
+            barrier()
+            os._exit(0)
         return
 
+    trace("e2e")
     # ---- end to end through the public API with host buffers (H2D of the step's inputs + D2H of the loss)
     host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in inp.items()}
     for k in host:
@@ -329,6 +349,7 @@ def main():
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = cfg["B"] * world / (float(e2e_ms) * 1e-3)
 
+    trace("done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -340,9 +361,15 @@ def main():
                 "loss": float(loss.detach())}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL communicators captured in a CUDA graph can stall destroy_process_group(): release the
+        # graph first, drain, and leave without the collective teardown.
+        bufs.graph = None
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
