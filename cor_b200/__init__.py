@@ -10,3 +10,5 @@ All compute is in cor_b200/libcor_b200.so (build: ``python -m cor_b200.build``);
 or PyTorch fallback.  ``cor_b200.synth`` (numpy only) generates the benchmark inputs.
 """
 __version__ = "0.1.0"
+
+from ._lib import CorError  # noqa: E402,F401

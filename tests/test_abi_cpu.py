@@ -99,3 +99,43 @@ def test_mask_adapter_parameter_names_match_reference_checkpoints():
                 mask_adatpet_network_mid_channel=32, num_output_maps=8)
         assert {k: tuple(v.shape) for k, v in r.state_dict().items()} == {k: tuple(v.shape) for k, v in m.state_dict().items()}
         m.load_state_dict(r.state_dict(), strict=True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only exists in the build container")
+def test_hooks_install_into_the_real_reference():
+    """hooks.install() rebinds the reference's own names; SupportBranch (support_branch.py:29-40) then
+    builds with the patched pooling classes, parameters and error behaviour untouched."""
+    import sys
+    import types
+    sys.path.insert(0, "/root/reference")
+    for name in ("open_clip", "accelerate"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.Accelerator = object
+            m.DistributedType = types.SimpleNamespace(MULTI_GPU="MULTI_GPU", DEEPSPEED="DEEPSPEED")
+            sys.modules[name] = m
+    from cor_b200 import hooks, loss_func, mask_adapter
+    import utils.loss_func as ref_lf
+    import lib.support_model.mask_adapter as ref_ma
+    import lib.support_model.siglip_openclip as ref_sig
+    orig = ref_lf.wbce_with_wiou_loss
+    done = hooks.install()
+    try:
+        assert "utils.loss_func" in done and "lib.support_model.mask_adapter" in done
+        assert ref_lf.wbce_with_wiou_loss is loss_func.wbce_with_wiou_loss
+        assert ref_lf.fg_feat_similarity_loss is loss_func.fg_feat_similarity_loss
+        ref_sig.SigLIP = lambda *a, **k: torch.nn.Identity()
+        import lib.support_branch as sb
+        sb.SigLIP = ref_sig.SigLIP
+        branch = sb.SupportBranch("ViT-B-16-SigLIP-384", "unused", mask_pooling="MaskAdapterPooling")
+        assert any(k.startswith("mask_pooling.get_mask_map.") for k in branch.state_dict())
+        with pytest.raises(_lib.CorError, match="no CPU fallback"):      # the patched forward is the CUDA path
+            branch.mask_pooling(torch.randn(1, 768, 24, 24), torch.rand(1, 1, 24, 24))
+        with pytest.raises(ValueError):
+            sb.SupportBranch("ViT-B-16-SigLIP-384", "unused", mask_pooling="nope")
+        assert type(sb.SupportBranch("ViT-B-16-SigLIP-384", "unused", mask_pooling="MaskedPooling").mask_pooling).forward \
+            is hooks._masked_forward
+    finally:
+        hooks.uninstall()
+    assert ref_lf.wbce_with_wiou_loss is orig
+    assert ref_ma.MaskedPooling.forward is not hooks._masked_forward
