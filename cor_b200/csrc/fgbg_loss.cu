@@ -17,14 +17,14 @@ namespace cor {
 constexpr float kCosEps = 1e-8f;  // F.cosine_similarity default eps
 
 // aux layout: rowstat [n][8] = {cos_fg, cos_bg, N_fg, N_bg, N_q, valid_fg, valid_bg, 0}; then colstat [3][C]
-__global__ void __launch_bounds__(128) fgbg_rows_kernel(const float* __restrict__ fg, const float* __restrict__ bg, long long row_stride,
-                                                        const float* __restrict__ comb, long long comb_stride,
+__global__ void __launch_bounds__(128) fgbg_rows_kernel(const float* __restrict__ fg, long long row_stride, const float* __restrict__ bg,
+                                                        long long bg_stride, const float* __restrict__ comb, long long comb_stride,
                                                         const float* __restrict__ stats, long long stats_stride, int C,
                                                         float* __restrict__ rowstat) {
   __shared__ float scratch[5 * 32];
   const int i = blockIdx.x;
   const float* f = fg + i * row_stride;
-  const float* g = bg ? bg + i * row_stride : nullptr;
+  const float* g = bg ? bg + i * bg_stride : nullptr;
   const float* q = comb + i * comb_stride;
   float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // f.q, g.q, f.f, g.g, q.q
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) fgbg_rows_kernel(const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(1024) fgbg_reduce_kernel(const float* __restrict__ bg, long long row_stride, const float* __restrict__ comb,
+__global__ void __launch_bounds__(1024) fgbg_reduce_kernel(const float* __restrict__ bg, long long bg_stride, const float* __restrict__ comb,
                                                            long long comb_stride, int n, int C, int bg_mode,
                                                            const float* __restrict__ rowstat, float* __restrict__ colstat,
                                                            float* __restrict__ out4) {
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(1024) fgbg_reduce_kernel(const float* __restri
       float A = 0.f, S1 = 0.f, ss = 0.f;
       for (int i = 0; i < n; ++i) {
         if (rowstat[(long long)i * 8 + 6] > 0.f) {
-          const float x = bg[i * row_stride + c], q = comb[i * comb_stride + c];
+          const float x = bg[i * bg_stride + c], q = comb[i * comb_stride + c];
           A += x / fmaxf(sq * fabsf(x), kCosEps);
           S1 += q;
           ss = fmaf(q, q, ss);
@@ -87,11 +87,13 @@ __global__ void __launch_bounds__(1024) fgbg_reduce_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(128) fgbg_bwd_kernel(const float* __restrict__ fg, const float* __restrict__ bg, long long row_stride,
-                                                       const float* __restrict__ comb, long long comb_stride, int C, int bg_mode,
-                                                       const float* __restrict__ rowstat, const float* __restrict__ colstat,
+__global__ void __launch_bounds__(128) fgbg_bwd_kernel(const float* __restrict__ fg, long long row_stride, const float* __restrict__ bg,
+                                                       long long bg_stride, const float* __restrict__ comb, long long comb_stride, int C,
+                                                       int bg_mode, const float* __restrict__ rowstat, const float* __restrict__ colstat,
                                                        const float* __restrict__ out4, const float* __restrict__ g2,
-                                                       float* __restrict__ g_fg, float* __restrict__ g_bg, float* __restrict__ g_comb) {
+                                                       float* __restrict__ g_fg, long long gfg_stride, int fg_acc,
+                                                       float* __restrict__ g_bg, long long gbg_stride, float* __restrict__ g_comb,
+                                                       long long gcomb_stride, int comb_acc) {
   const int i = blockIdx.x;
   const float* r = rowstat + (long long)i * 8;
   const float nfg = out4[2], nbg = out4[3];
@@ -101,9 +103,11 @@ __global__ void __launch_bounds__(128) fgbg_bwd_kernel(const float* __restrict__
   const float cf = r[0], cb = r[1], nf = r[2], nb = r[3], nq = r[4];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float a = fg[i * row_stride + c], x = comb[i * comb_stride + c];
-    const float b = bg ? bg[i * row_stride + c] : 0.f;
+    const float b = bg ? bg[i * bg_stride + c] : 0.f;
     float gq = sf * (a / (nf * nq) - cf * x / (nq * nq));
-    g_fg[(long long)i * C + c] = sf * (x / (nf * nq) - cf * a / (nf * nf));
+    const float ga = sf * (x / (nf * nq) - cf * a / (nf * nf));
+    float* pf = g_fg + i * gfg_stride + c;
+    *pf = fg_acc ? *pf + ga : ga;
     float gb = 0.f;
     if (sb != 0.f) {
       gb = sb * (x / (nb * nq) - cb * b / (nb * nb));
@@ -113,9 +117,16 @@ __global__ void __launch_bounds__(128) fgbg_bwd_kernel(const float* __restrict__
       const float A = colstat[c], S1 = colstat[C + c], s2 = colstat[2 * C + c];
       gq += quirk * A * (1.f / s2 - S1 * x / (s2 * s2 * s2));
     }
-    if (g_bg) g_bg[(long long)i * C + c] = gb;
-    g_comb[(long long)i * C + c] = gq;
+    if (g_bg) g_bg[i * gbg_stride + c] = gb;
+    float* pq = g_comb + i * gcomb_stride + c;
+    *pq = comb_acc ? *pq + gq : gq;
   }
+}
+
+// loss = seg + w_fg * fg + w_bg * bg + w_nce * nce  (utils/trainer_v3_g.py:67-73 plus the Class-N term)
+__global__ void step_combine_kernel(const float* seg, const float* fgbg, const float* nce, float w_fg, float w_bg, float w_nce,
+                                    float* loss) {
+  loss[0] = seg[0] + w_fg * fgbg[0] + w_bg * fgbg[1] + (nce ? w_nce * nce[0] : 0.f);
 }
 
 }  // namespace cor
@@ -124,24 +135,33 @@ using namespace cor;
 
 extern "C" size_t cor_fgbg_aux_floats(int n, int C) { return (size_t)n * 8 + (size_t)3 * C; }
 
-extern "C" int cor_fgbg_loss_fwd(const float* fg_rows, const float* bg_rows, long long row_stride, const float* comb,
+extern "C" int cor_fgbg_loss_fwd(const float* fg_rows, long long fg_stride, const float* bg_rows, long long bg_stride, const float* comb,
                                  long long comb_stride, const float* stats, long long stats_stride, int n, int C, int bg_mode,
                                  float* out4, float* aux, cor_stream_t stream) {
   COR_REQUIRE(fg_rows && comb && stats && out4 && aux, "cor_fgbg_loss_fwd: null pointer");
   COR_REQUIRE(n > 0 && C > 0 && (bg_mode == 0 || bg_mode == 1), "cor_fgbg_loss_fwd: bad arguments n=%d C=%d mode=%d", n, C, bg_mode);
   cudaStream_t st = as_stream(stream);
-  fgbg_rows_kernel<<<n, 128, 0, st>>>(fg_rows, bg_rows, row_stride, comb, comb_stride, stats, stats_stride, C, aux);
+  fgbg_rows_kernel<<<n, 128, 0, st>>>(fg_rows, fg_stride, bg_rows, bg_stride, comb, comb_stride, stats, stats_stride, C, aux);
   int rc = check_launch("fgbg_rows_kernel");
   if (rc) return rc;
-  fgbg_reduce_kernel<<<1, 1024, 0, st>>>(bg_rows, row_stride, comb, comb_stride, n, C, bg_mode, aux, aux + (size_t)n * 8, out4);
+  fgbg_reduce_kernel<<<1, 1024, 0, st>>>(bg_rows, bg_stride, comb, comb_stride, n, C, bg_mode, aux, aux + (size_t)n * 8, out4);
   return check_launch("fgbg_reduce_kernel");
 }
 
-extern "C" int cor_fgbg_loss_bwd(const float* fg_rows, const float* bg_rows, long long row_stride, const float* comb,
-                                 long long comb_stride, int n, int C, int bg_mode, const float* out4, const float* aux,
-                                 const float* g2, float* g_fg_rows, float* g_bg_rows, float* g_comb, cor_stream_t stream) {
+extern "C" int cor_fgbg_loss_bwd(const float* fg_rows, long long fg_stride, const float* bg_rows, long long bg_stride, const float* comb,
+                                 long long comb_stride, int n, int C, int bg_mode, const float* out4, const float* aux, const float* g2,
+                                 float* g_fg_rows, long long gfg_stride, int fg_accumulate, float* g_bg_rows, long long gbg_stride,
+                                 float* g_comb, long long gcomb_stride, int comb_accumulate, cor_stream_t stream) {
   COR_REQUIRE(fg_rows && comb && out4 && aux && g2 && g_fg_rows && g_comb, "cor_fgbg_loss_bwd: null pointer");
-  fgbg_bwd_kernel<<<n, 128, 0, as_stream(stream)>>>(fg_rows, bg_rows, row_stride, comb, comb_stride, C, bg_mode, aux,
-                                                    aux + (size_t)n * 8, out4, g2, g_fg_rows, g_bg_rows, g_comb);
+  fgbg_bwd_kernel<<<n, 128, 0, as_stream(stream)>>>(fg_rows, fg_stride, bg_rows, bg_stride, comb, comb_stride, C, bg_mode, aux,
+                                                    aux + (size_t)n * 8, out4, g2, g_fg_rows, gfg_stride, fg_accumulate, g_bg_rows,
+                                                    gbg_stride, g_comb, gcomb_stride, comb_accumulate);
   return check_launch("fgbg_bwd_kernel");
+}
+
+extern "C" int cor_step_combine(const float* seg, const float* fgbg, const float* nce, float w_fg, float w_bg, float w_nce, float* loss,
+                                cor_stream_t stream) {
+  COR_REQUIRE(seg && fgbg && loss, "cor_step_combine: null pointer");
+  step_combine_kernel<<<1, 1, 0, as_stream(stream)>>>(seg, fgbg, nce, w_fg, w_bg, w_nce, loss);
+  return check_launch("step_combine_kernel");
 }

@@ -54,18 +54,31 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_umma_kernel(const float* __re
   if (warp == 1) tmem_alloc(tmem_slot, kGN);
 
   // ---- B operand: w[p][r] (row = pixel, K = mask) from the fp32 weights, transform on the fly -------
+  // The build is pure load latency: keep 32 independent loads in flight per thread before packing.
   {
     const int p = threadIdx.x;                               // 256 threads <-> 256 pixels of the tile
     const float* wp = wts + (long long)b * R * ldw + p0 + p;
-    for (int r8 = 0; r8 < Kp / 8; ++r8) {
-      float v[8];
+    for (int rb = 0; rb < Kp; rb += 32) {
+      float v[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = r8 * 8 + j;
-        v[j] = r < R ? transform_wb(__ldg(wp + (long long)r * ldw), transform) : ((has_bg && r == R) ? 1.f : 0.f);
+      for (int j = 0; j < 32; ++j) {
+        const int r = rb + j;
+        v[j] = r < R ? __ldg(wp + (long long)r * ldw) : 0.f;
       }
-      uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(b_smem + (size_t)(r8 >> 3) * kGN * 128 + sw128_off(p, r8 & 7)) = q;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int r8 = (rb >> 3) + g;
+        if (r8 * 8 < Kp) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = r8 * 8 + j;
+            t[j] = r < R ? transform_wb(v[g * 8 + j], transform) : ((has_bg && r == R) ? 1.f : 0.f);
+          }
+          uint4 q = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+          *reinterpret_cast<uint4*>(b_smem + (size_t)(r8 >> 3) * kGN * 128 + sw128_off(p, r8 & 7)) = q;
+        }
+      }
     }
   }
   // ---- A operand: (g_fg - g_bg)[c][r] (row = channel, K = mask); ones-row column = sum_r g_bg[r][c] ---
@@ -75,20 +88,38 @@ __global__ void __launch_bounds__(256, 2) pool_bwd_umma_kernel(const float* __re
     const float* gb = has_bg ? g_bg + (long long)b * R * C + c0 + c : nullptr;
     float bgsum = 0.f;
     if (has_bg && (R / 8) % 2 == half) {                     // the thread half that will write column R
-      for (int r = 0; r < R; ++r) bgsum += __ldg(gb + (long long)r * C);
-    }
-    for (int r8 = half; r8 < Kp / 8; r8 += 2) {
-      float v[8];
+      float part8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < R; r += 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = r8 * 8 + j;
-        float x = 0.f;
-        if (r < R) x = __ldg(gf + (long long)r * C) - (has_bg ? __ldg(gb + (long long)r * C) : 0.f);
-        else if (has_bg && r == R) x = bgsum;
-        v[j] = x;
+        for (int j = 0; j < 8; ++j)
+          if (r + j < R) part8[j] += __ldg(gb + (long long)(r + j) * C);
       }
-      uint4 q = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(a_smem + (size_t)(r8 >> 3) * kGM * 128 + sw128_off(c, r8 & 7)) = q;
+      bgsum = ((part8[0] + part8[1]) + (part8[2] + part8[3])) + ((part8[4] + part8[5]) + (part8[6] + part8[7]));
+    }
+    for (int r8 = half; r8 < Kp / 8; r8 += 4) {              // two 8-groups (r8, r8+2) per round: 32 loads in flight
+      float vf[2][8], vb[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = (r8 + 2 * u) * 8 + j;
+          vf[u][j] = r < R ? __ldg(gf + (long long)r * C) : 0.f;
+          vb[u][j] = (has_bg && r < R) ? __ldg(gb + (long long)r * C) : 0.f;
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g8 = r8 + 2 * u;
+        if (g8 < Kp / 8) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = g8 * 8 + j;
+            t[j] = r < R ? vf[u][j] - vb[u][j] : ((has_bg && r == R) ? bgsum : 0.f);
+          }
+          uint4 q = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+          *reinterpret_cast<uint4*>(a_smem + (size_t)(g8 >> 3) * kGM * 128 + sw128_off(c, g8 & 7)) = q;
+        }
+      }
     }
   }
   fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)

@@ -22,9 +22,36 @@ struct SegSmem {
   float hs[kTH * kHS];
 };
 
-template <typename TP, typename TM>
+// One bilinear sample of the mask at logit pixel (gy, gx): issue the loads (tap values into v[4]) ...
+template <typename TM>
+__device__ __forceinline__ void tap_load(const TM* __restrict__ mbase, int Hm, int Wm, float sh, float sw, int gy, int gx, bool same,
+                                         float (&v)[4], float (&l)[4]) {
+  if (same) {
+    v[0] = to_f<TM>(__ldg(mbase + (long long)gy * Wm + gx));
+    v[1] = v[2] = v[3] = 0.f;
+    l[0] = 1.f; l[1] = 0.f; l[2] = 1.f; l[3] = 0.f;
+    return;
+  }
+  int y0, y1, x0, x1;
+  src_index(sh, gy, Hm, y0, y1, l[0], l[1]);
+  src_index(sw, gx, Wm, x0, x1, l[2], l[3]);
+  const TM* r0 = mbase + (long long)y0 * Wm;
+  const TM* r1 = mbase + (long long)y1 * Wm;
+  v[0] = to_f<TM>(__ldg(r0 + x0)); v[1] = to_f<TM>(__ldg(r0 + x1));
+  v[2] = to_f<TM>(__ldg(r1 + x0)); v[3] = to_f<TM>(__ldg(r1 + x1));
+}
+// ... and combine them exactly like ATen's upsample_bilinear2d: ly0*(lx0*v00 + lx1*v01) + ly1*(lx0*v10 + lx1*v11)
+__device__ __forceinline__ float tap_combine(const float (&v)[4], const float (&l)[4]) {
+  return l[0] * (l[2] * v[0] + l[3] * v[1]) + l[1] * (l[2] * v[2] + l[3] * v[3]);
+}
+
+constexpr int kFill = 4;   // halo pixels whose taps are in flight per thread (memory-level parallelism)
+
+// FAST4: fp32 mask at exactly 4x the logit resolution (the shipped 1024^2 -> 256^2 case): the 2x2 taps of
+// pixel (gy,gx) are elements .y/.z of the aligned float4 at column 4*gx in rows 4*gy+1 and 4*gy+2.
+template <typename TP, typename TM, bool FAST4>
 __global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict__ pred, const TM* __restrict__ mask, float mscale, int H,
-                                                            int W, int Hm, int Wm, float focal_alpha, float focal_gamma,
+                                                            int W, int Hm, int Wm, long long mask_nstride, float focal_alpha, float focal_gamma,
                                                             float* __restrict__ t_save, float* __restrict__ w_save,
                                                             double* __restrict__ part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -36,28 +63,44 @@ __global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict
   const int ty0 = (tile / tiles_x) * kT, tx0 = (tile % tiles_x) * kT;
   const bool same = (Hm == H && Wm == W);
   const float sh = (float)Hm / (float)H, sw = (float)Wm / (float)W;
-  const TM* mbase = mask + (long long)n * Hm * Wm;
+  const TM* mbase = mask + (long long)n * mask_nstride;
 
-  // 1. target tile with halo (zero outside the image: avg_pool2d zero padding, count_include_pad)
-  for (int i = threadIdx.x; i < kTH * kTH; i += blockDim.x) {
-    const int hy = i / kTH, hx = i % kTH;
-    const int gy = ty0 + hy - kHalo, gx = tx0 + hx - kHalo;
-    float v = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      if (same) {
-        v = to_f<TM>(__ldg(mbase + (long long)gy * Wm + gx)) * mscale;
-      } else {
-        int y0, y1, x0, x1;
-        float ly0, ly1, lx0, lx1;
-        src_index(sh, gy, Hm, y0, y1, ly0, ly1);
-        src_index(sw, gx, Wm, x0, x1, lx0, lx1);
-        const TM* r0 = mbase + (long long)y0 * Wm;
-        const TM* r1 = mbase + (long long)y1 * Wm;
-        v = (ly0 * (lx0 * to_f<TM>(__ldg(r0 + x0)) + lx1 * to_f<TM>(__ldg(r0 + x1))) +
-             ly1 * (lx0 * to_f<TM>(__ldg(r1 + x0)) + lx1 * to_f<TM>(__ldg(r1 + x1)))) * mscale;
+  // 0. prefetch this thread's 16 logits (consumed in step 3) so their latency hides behind steps 1-2
+  const int px = threadIdx.x & 63, py0 = (threadIdx.x >> 6) * 16;
+  float z[16];
+#pragma unroll
+  for (int y = 0; y < 16; ++y) {
+    const int gy = ty0 + py0 + y, gx = tx0 + px;
+    z[y] = (gy < H && gx < W) ? to_f<TP>(__ldg(pred + ((long long)n * H + gy) * W + gx)) : 0.f;
+  }
+
+  // 1. target tile with halo (zero outside the image: avg_pool2d zero padding, count_include_pad);
+  //    kFill pixels per thread are gathered before any is consumed
+  for (int i0 = threadIdx.x; i0 < kTH * kTH; i0 += kFill * blockDim.x) {
+    float v[kFill][4], l[kFill][4];
+    bool ok[kFill];
+#pragma unroll
+    for (int u = 0; u < kFill; ++u) {
+      const int i = i0 + u * blockDim.x;
+      const int hy = i / kTH, hx = i % kTH;
+      const int gy = ty0 + hy - kHalo, gx = tx0 + hx - kHalo;
+      ok[u] = i < kTH * kTH && gy >= 0 && gy < H && gx >= 0 && gx < W;
+      if (ok[u]) {
+        if (FAST4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(mbase + (long long)(4 * gy + 1) * Wm) + gx);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(mbase + (long long)(4 * gy + 2) * Wm) + gx);
+          v[u][0] = a.y; v[u][1] = a.z; v[u][2] = b.y; v[u][3] = b.z;
+          l[u][0] = l[u][1] = l[u][2] = l[u][3] = 0.5f;
+        } else {
+          tap_load<TM>(mbase, Hm, Wm, sh, sw, gy, gx, same, v[u], l[u]);
+        }
       }
     }
-    sm.t[hy * kTS + hx] = v;
+#pragma unroll
+    for (int u = 0; u < kFill; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i < kTH * kTH) sm.t[(i / kTH) * kTS + (i % kTH)] = ok[u] ? tap_combine(v[u], l[u]) * mscale : 0.f;
+    }
   }
   __syncthreads();
 
@@ -79,28 +122,28 @@ __global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict
 
   // 3. vertical 31-sums + per-pixel terms: thread = (column, segment of 16 rows)
   double acc[kNP];
-#pragma unroll
-  for (int k = 0; k < kNP; ++k) acc[k] = 0.0;
   {
-    const int x = threadIdx.x & 63, y0 = (threadIdx.x >> 6) * 16;
+    const int x = px, y0 = py0;
     const int gx = tx0 + x;
+    const bool want_focal = focal_gamma >= 0.f;
     float s = 0.f;
 #pragma unroll
     for (int d = 0; d < 31; ++d) s += sm.hs[(y0 + d) * kHS + x];
     float f[kNP];
 #pragma unroll
     for (int k = 0; k < kNP; ++k) f[k] = 0.f;
+#pragma unroll
     for (int y = 0; y < 16; ++y) {
       if (y > 0) s += sm.hs[(y0 + y + 30) * kHS + x] - sm.hs[(y0 + y - 1) * kHS + x];
       const int gy = ty0 + y0 + y;
       if (gy < H && gx < W) {
         const float t = sm.t[(y0 + y + kHalo) * kTS + x + kHalo];
         const float wgt = 1.f + 5.f * fabsf(s * (1.f / 961.f) - t);
-        const long long o = ((long long)n * H + gy) * W + gx;
-        const float z = to_f<TP>(__ldg(pred + o));
-        const float e = expf(-fabsf(z));
-        const float bce = (1.f - t) * z - (fminf(z, 0.f) - log1pf(e));
-        const float p = z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+        const float zz = z[y];
+        const float e = __expf(-fabsf(zz));
+        const float bce = (1.f - t) * zz - (fminf(zz, 0.f) - __logf(1.f + e));   // (1-t)x - logsigmoid(x)
+        const float inv = __fdividef(1.f, 1.f + e);
+        const float p = zz >= 0.f ? inv : e * inv;
         f[0] += wgt;
         f[1] = fmaf(wgt, bce, f[1]);
         f[2] = fmaf(p * t, wgt, f[2]);
@@ -108,10 +151,16 @@ __global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict
         f[4] = fmaf(p, t, f[4]);
         f[5] += p;
         f[6] += t;
-        const float pt = p * t + (1.f - p) * (1.f - t);
-        const float at = focal_alpha * t + (1.f - focal_alpha) * (1.f - t);
-        f[7] = fmaf(at * __powf(fmaxf(1.f - pt, 0.f), focal_gamma), bce, f[7]);
-        if (t_save) { t_save[o] = t; w_save[o] = wgt; }
+        if (want_focal) {
+          const float pt = p * t + (1.f - p) * (1.f - t);
+          const float at = focal_alpha * t + (1.f - focal_alpha) * (1.f - t);
+          f[7] = fmaf(at * __powf(fmaxf(1.f - pt, 0.f), focal_gamma), bce, f[7]);
+        }
+        if (t_save) {
+          const long long o = ((long long)n * H + gy) * W + gx;
+          t_save[o] = t;
+          w_save[o] = wgt;
+        }
       }
     }
 #pragma unroll
@@ -130,21 +179,29 @@ __global__ void __launch_bounds__(256) seg_loss_finalize_kernel(const double* __
                                                                 float w2, float dice_smooth, float* __restrict__ per_sample,
                                                                 float* __restrict__ out8) {
   __shared__ double scratch[5 * 32];
+  __shared__ double ssum[32][kNP];          // per-sample tile sums for a batch of 32 samples
   double v[5] = {0, 0, 0, 0, 0};
-  for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    double s[kNP];
-    for (int k = 0; k < kNP; ++k) s[k] = 0.0;
-    for (int t = 0; t < tiles; ++t)
-      for (int k = 0; k < kNP; ++k) s[k] += part[((long long)n * tiles + t) * kNP + k];
-    for (int k = 0; k < kNP; ++k) per_sample[(long long)n * kNP + k] = (float)s[k];
-    const double wbce = s[1] / s[0];
-    const double inter = s[2], uni = s[3] - s[2];
-    const double wiou = 1.0 - (inter + 1e-6) / (uni + 1e-6);
-    v[0] += (double)w1 * wbce + (double)w2 * wiou;
-    v[1] += 1.0 - (2.0 * s[4] + dice_smooth) / (s[5] + s[6] + dice_smooth);
-    v[2] += s[7];
-    v[3] += wbce;
-    v[4] += wiou;
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    // thread (s, k) = (sample n0 + tid / 8, partial k = tid % 8) folds the tiles in fixed order
+    const int sidx = threadIdx.x >> 3, k = threadIdx.x & 7, n = n0 + sidx;
+    double acc = 0.0;
+    if (n < N)
+      for (int t = 0; t < tiles; ++t) acc += part[((long long)n * tiles + t) * kNP + k];
+    ssum[sidx][k] = acc;
+    if (n < N) per_sample[(long long)n * kNP + k] = (float)acc;
+    __syncthreads();
+    if (threadIdx.x < 32 && n0 + threadIdx.x < N) {
+      const double* s = ssum[threadIdx.x];
+      const double wbce = s[1] / s[0];
+      const double inter = s[2], uni = s[3] - s[2];
+      const double wiou = 1.0 - (inter + 1e-6) / (uni + 1e-6);
+      v[0] += (double)w1 * wbce + (double)w2 * wiou;
+      v[1] += 1.0 - (2.0 * s[4] + dice_smooth) / (s[5] + s[6] + dice_smooth);
+      v[2] += s[7];
+      v[3] += wbce;
+      v[4] += wiou;
+    }
+    __syncthreads();
   }
   block_sum<5>(v, scratch);
   if (threadIdx.x == 0) {
@@ -178,18 +235,26 @@ __global__ void __launch_bounds__(256) seg_loss_bwd_kernel(const TP* __restrict_
   }
 }
 
-template <typename TP, typename TM>
-static int launch_tiles(const void* pred, const void* mask, float mscale, int N, int H, int W, int Hm, int Wm, float fa, float fg_,
-                        float* t_save, float* w_save, double* part, cudaStream_t st) {
+template <typename TP, typename TM, bool FAST4>
+static int launch_tiles_impl(const void* pred, const void* mask, float mscale, int N, int H, int W, int Hm, int Wm, long long ns, float fa, float fg_,
+                             float* t_save, float* w_save, double* part, cudaStream_t st) {
   const int tiles = ceil_div(H, kT) * ceil_div(W, kT);
-  auto k = seg_loss_tile_kernel<TP, TM>;
+  auto k = seg_loss_tile_kernel<TP, TM, FAST4>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SegSmem));
   if (e != cudaSuccess) {
     set_error("seg_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return COR_ECUDA;
   }
-  k<<<N * tiles, 256, sizeof(SegSmem), st>>>((const TP*)pred, (const TM*)mask, mscale, H, W, Hm, Wm, fa, fg_, t_save, w_save, part);
+  k<<<N * tiles, 256, sizeof(SegSmem), st>>>((const TP*)pred, (const TM*)mask, mscale, H, W, Hm, Wm, ns, fa, fg_, t_save, w_save, part);
   return check_launch("seg_loss_tile_kernel");
+}
+
+template <typename TP, typename TM>
+static int launch_tiles(const void* pred, const void* mask, float mscale, int N, int H, int W, int Hm, int Wm, long long ns, float fa, float fg_,
+                        float* t_save, float* w_save, double* part, cudaStream_t st) {
+  if (sizeof(TM) == 4 && Hm == 4 * H && Wm == 4 * W && (((uintptr_t)mask) & 15) == 0 && ns % 4 == 0)
+    return launch_tiles_impl<TP, float, true>(pred, mask, mscale, N, H, W, Hm, Wm, ns, fa, fg_, t_save, w_save, part, st);
+  return launch_tiles_impl<TP, TM, false>(pred, mask, mscale, N, H, W, Hm, Wm, ns, fa, fg_, t_save, w_save, part, st);
 }
 
 }  // namespace cor
@@ -201,7 +266,7 @@ extern "C" size_t cor_seg_loss_work_bytes(int N, int H, int W) {
 }
 
 extern "C" int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* mask, int mask_dtype, float mask_scale, int N,
-                                int H, int W, int Hm, int Wm, float w1, float w2, float focal_alpha, float focal_gamma,
+                                int H, int W, int Hm, int Wm, long long mask_nstride, float w1, float w2, float focal_alpha, float focal_gamma,
                                 float dice_smooth, float* out8, float* per_sample, float* t_save, float* w_save, void* work,
                                 cor_stream_t stream) {
   COR_REQUIRE(pred && mask && out8 && per_sample && work, "cor_seg_loss_fwd: null pointer");
@@ -210,7 +275,9 @@ extern "C" int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* ma
   cudaStream_t st = as_stream(stream);
   double* part = reinterpret_cast<double*>(work);
   int rc = COR_EINVAL;
-#define COR_SEG(TP, TM) rc = launch_tiles<TP, TM>(pred, mask, mask_scale, N, H, W, Hm, Wm, focal_alpha, focal_gamma, t_save, w_save, part, st)
+  if (mask_nstride <= 0) mask_nstride = (long long)Hm * Wm;
+  COR_REQUIRE(mask_nstride >= (long long)Hm * Wm, "cor_seg_loss_fwd: mask_nstride too small");
+#define COR_SEG(TP, TM) rc = launch_tiles<TP, TM>(pred, mask, mask_scale, N, H, W, Hm, Wm, mask_nstride, focal_alpha, focal_gamma, t_save, w_save, part, st)
   if (pred_dtype == COR_F32 && mask_dtype == COR_F32) COR_SEG(float, float);
   else if (pred_dtype == COR_BF16 && mask_dtype == COR_F32) COR_SEG(bf16, float);
   else if (pred_dtype == COR_F32 && mask_dtype == COR_U8) COR_SEG(float, uint8_t);

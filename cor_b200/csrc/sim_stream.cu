@@ -110,21 +110,24 @@ __global__ void __launch_bounds__(256) sim_stream_kernel(const bf16* __restrict_
   }
 }
 
-// lse[q] = log sum_r exp(S[q,r]/tau): fixed-order merge of `nparts` (max,sum) partials per query.
+// lse[q] = log sum_r exp(S[q,r]/tau): merge of `nparts` (max,sum) partials per query, one warp per query
+// (lanes stride over the partials, butterfly max / sum: fixed order, deterministic).
 // part layout [qtiles][nparts][qt][2]; works for both the streaming and the UMMA producer.
-__global__ void sim_lse_combine_kernel(const float* __restrict__ part, int Nq, int nparts, int qt, float* __restrict__ lse) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) sim_lse_combine_kernel(const float* __restrict__ part, int Nq, int nparts, int qt, float* __restrict__ lse) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= Nq) return;
   const int tile = q / qt, ql = q % qt;
   const float* base = part + ((long long)tile * nparts * qt + ql) * 2;
   float M = -INFINITY;
-  for (int p = 0; p < nparts; ++p) M = fmaxf(M, base[(long long)p * qt * 2]);
+  for (int p = lane; p < nparts; p += 32) M = fmaxf(M, base[(long long)p * qt * 2]);
+  M = warp_max(M);
   double acc = 0.0;
-  for (int p = 0; p < nparts; ++p) {
+  for (int p = lane; p < nparts; p += 32) {
     const float pm = base[(long long)p * qt * 2], ps = base[(long long)p * qt * 2 + 1];
     if (pm != -INFINITY) acc += (double)ps * exp((double)pm - (double)M);
   }
-  lse[q] = M + (float)log(acc);
+  acc = warp_sum(acc);
+  if (lane == 0) lse[q] = M + (float)log(acc);
 }
 
 // ---- InfoNCE forward: target logits and the mean loss ------------------------------------------------
@@ -253,12 +256,21 @@ __global__ void __launch_bounds__(256, 1) infonce_bwd_kernel(const bf16* __restr
   }
 }
 
-__global__ void infonce_bwd_q_kernel(const float* __restrict__ qpart, int nparts, long long n, float* __restrict__ g_queries) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// g_queries[i] = sum_p qpart[p][i]: block (32, 8) -- 8 thread rows split the partials, fixed-order smem fold
+__global__ void __launch_bounds__(256) infonce_bwd_q_kernel(const float* __restrict__ qpart, int nparts, long long n, float* __restrict__ g_queries) {
+  __shared__ float red[8][33];
+  const long long i = (long long)blockIdx.x * 32 + threadIdx.x;
   float t = 0.f;
-  for (int p = 0; p < nparts; ++p) t += qpart[(long long)p * n + i];
-  g_queries[i] = t;
+  if (i < n)
+    for (int p = threadIdx.y; p < nparts; p += 8) t += qpart[(long long)p * n + i];
+  red[threadIdx.y][threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    float a = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) a += red[y][threadIdx.x];
+    g_queries[i] = a;
+  }
 }
 
 // ---- top-k: radix select on the prefilter scores, exact fp64 re-score, bitonic sort -----------------------
@@ -381,7 +393,7 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ S, 
 
 namespace cor {
 int launch_lse_combine(const float* part, int Nq, int nparts, int qt, float* lse, cudaStream_t st) {
-  sim_lse_combine_kernel<<<ceil_div(Nq, 128), 128, 0, st>>>(part, Nq, nparts, qt, lse);
+  sim_lse_combine_kernel<<<ceil_div(Nq, 8), 256, 0, st>>>(part, Nq, nparts, qt, lse);
   return check_launch("sim_lse_combine_kernel");
 }
 }  // namespace cor
@@ -455,7 +467,7 @@ extern "C" int cor_infonce_bwd(const void* regions, const void* queries, const l
   int rc = check_launch("infonce_bwd_kernel");
   if (rc) return rc;
   const long long n = (long long)Nq * D;
-  infonce_bwd_q_kernel<<<ceil_div(n, 256), 256, 0, st>>>((const float*)work, ctas, n, g_queries);
+  infonce_bwd_q_kernel<<<ceil_div(n, 32), dim3(32, 8), 0, st>>>((const float*)work, ctas, n, g_queries);
   return check_launch("infonce_bwd_q_kernel");
 }
 

@@ -2,30 +2,37 @@
 // epilogue (Class N; no reference implementation -- the reference's F.cosine_similarity at
 // utils/loss_func.py:84,123 is the diagonal of this matrix).
 //
-//   S[q, r] = sum_d Q[q,d] * R[r,d]          Q: queries, A operand, 128 rows resident in shared memory
-//                                            R: regions, B operand, 256 rows x 64 d per TMA stage
+//   S[q, r] = sum_d Q[q,d] * R[r,d]          Q: queries, A operand, up to 256 rows resident in shared memory
+//                                            R: regions, B operand, 128 rows x 64 d per TMA stage
 //   lse[q]  = log sum_r exp(S[q,r] / tau)    accumulated on line by the thread that owns TMEM lane q
 //
 // Orientation: queries on the MMA M axis (TMEM lanes), regions on N (TMEM columns).  An epilogue thread
 // therefore owns one query row: its running (max, sum) is two registers, and the optional S store is
-// 64 contiguous bytes per thread per 16-column chunk.  Persistent CTAs walk region tiles with a 4-stage
-// TMA ring and a double-buffered TMEM accumulator (2 x 256 columns), so the MMA of tile i+1 overlaps the
-// epilogue of tile i.  With few queries the kernel is HBM-bound on the region stream; with >= 128 queries
-// per tile it is tensor-pipe-bound.
+// 64 contiguous bytes per thread per 16-column chunk.
 //
-// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..5 = epilogue.
+// A CTA holds TWO 128-query halves and issues two M128 x N128 x K16 MMAs per region k-slice, so every
+// region byte fetched from L2 feeds 256 query rows (the region stream, not the tensor pipe, is what
+// saturates first at M = 128).  Persistent CTAs walk region tiles with a 5-stage TMA ring and a
+// double-buffered TMEM accumulator (2 buffers x 2 halves x 128 columns = all 512), so the MMAs of tile
+// i+1 overlap the epilogue of tile i.  With few queries the kernel is HBM-bound on the region stream;
+// with hundreds of queries it is tensor-pipe-bound.
+//
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue
+// (warp w reads TMEM lane quarter w % 4 of half (w - 2) / 4).
 #include "umma.cuh"
 
 namespace cor {
 
 using namespace umma;
 
-constexpr int kSimStages = 4;
-constexpr int kSimBM = 128;                     // queries per CTA tile (UMMA M)
-constexpr int kSimBN = 256;                     // regions per tile     (UMMA N)
+constexpr int kSimStages = 5;
+constexpr int kSimHalf = 128;                    // queries per MMA (UMMA M)
+constexpr int kSimBM = 2 * kSimHalf;             // queries per CTA
+constexpr int kSimBN = 128;                      // regions per tile (UMMA N)
 constexpr int kSimBK = 64;
-constexpr int kSimABytes = kSimBM * kSimBK * 2; // 16 KB per k-block of queries
-constexpr int kSimBBytes = kSimBN * kSimBK * 2; // 32 KB per stage of regions
+constexpr int kSimABytes = kSimHalf * kSimBK * 2;  // 16 KB: one k-block of one query half
+constexpr int kSimBBytes = kSimBN * kSimBK * 2;    // 16 KB: one stage of regions
+constexpr int kSimMaxKB = 4;                       // D <= 256
 
 struct SimSmemTail {
   uint64_t qfull, full[kSimStages], empty[kSimStages], acc_full[2], acc_empty[2];
@@ -33,17 +40,18 @@ struct SimSmemTail {
 };
 
 // part layout (shared with the streaming producer's combine kernel): [qtile][gridDim.x][kSimBM][2]
-__global__ void __launch_bounds__(192, 1) sim_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmR,
+__global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmR,
                                                           int Nr, int Nq, int nkb, float inv_tau, float* __restrict__ S,
                                                           float* __restrict__ part) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
-  uint8_t* q_smem = base;                                   // nkb x 16 KB
-  uint8_t* r_smem = base + 4 * kSimABytes;                  // kSimStages x 32 KB (q area sized for nkb <= 4)
+  uint8_t* q_smem = base;                                                   // [half][kb] x 16 KB
+  uint8_t* r_smem = base + 2 * kSimMaxKB * kSimABytes;                      // kSimStages x 16 KB
   SimSmemTail* tail = reinterpret_cast<SimSmemTail*>(r_smem + kSimStages * kSimBBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.y * kSimBM;
+  const int nhalf = (Nq - q0 > kSimHalf) ? 2 : 1;
   const int ntiles = (Nr + kSimBN - 1) / kSimBN;
 
   if (warp == 0 && lane == 0) {
@@ -51,7 +59,7 @@ __global__ void __launch_bounds__(192, 1) sim_umma_kernel(const __grid_constant_
     prefetch_tmap(&tmR);
     mbar_init(&tail->qfull, 1);
     for (int i = 0; i < kSimStages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tail->acc_full[i], 1); mbar_init(&tail->acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tail->acc_full[i], 1); mbar_init(&tail->acc_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tail->tmem_base, 512);
@@ -62,8 +70,10 @@ __global__ void __launch_bounds__(192, 1) sim_umma_kernel(const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&tail->qfull, (uint32_t)(nkb * kSimABytes));
-      for (int kb = 0; kb < nkb; ++kb) tma_load_2d(q_smem + kb * kSimABytes, &tmQ, &tail->qfull, kb * kSimBK, q0, kEvictLast);
+      mbar_expect_tx(&tail->qfull, (uint32_t)(nhalf * nkb * kSimABytes));
+      for (int hf = 0; hf < nhalf; ++hf)
+        for (int kb = 0; kb < nkb; ++kb)
+          tma_load_2d(q_smem + (hf * kSimMaxKB + kb) * kSimABytes, &tmQ, &tail->qfull, kb * kSimBK, q0 + hf * kSimHalf, kEvictLast);
       int it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -76,77 +86,107 @@ __global__ void __launch_bounds__(192, 1) sim_umma_kernel(const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kSimBM, kSimBN);
+      const uint32_t idesc = make_idesc_bf16(kSimHalf, kSimBN);
       mbar_wait(&tail->qfull, 0);
       int it = 0, i = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
         const int buf = i & 1;
         mbar_wait(&tail->acc_empty[buf], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_addr = tmem + (uint32_t)(buf * kSimBN);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int st = it % kSimStages;
           mbar_wait(&tail->full[st], (it / kSimStages) & 1);
           tc_fence_after();
-          const uint64_t da = make_desc_sw128(smem_u32(q_smem + kb * kSimABytes));
           const uint64_t db = make_desc_sw128(smem_u32(r_smem + st * kSimBBytes));
+          for (int hf = 0; hf < nhalf; ++hf) {
+            const uint64_t da = make_desc_sw128(smem_u32(q_smem + (hf * kSimMaxKB + kb) * kSimABytes));
+            const uint32_t d_addr = tmem + (uint32_t)((buf * 2 + hf) * kSimBN);
 #pragma unroll
-          for (int k = 0; k < kSimBK / 16; ++k) mma_bf16_ss(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kSimBK / 16; ++k) mma_bf16_ss(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
           mma_commit(&tail->empty[st]);
         }
         mma_commit(&tail->acc_full[buf]);
       }
     }
   } else {
+    const int e = warp - 2;
     const int qd = warp & 3;                       // TMEM lane quarter this warp may read
-    const int q = q0 + qd * 32 + lane;             // query row owned by this thread
-    const bool qok = q < Nq;
-    float m = -INFINITY, ssum = 0.f;
+    const int hf = e >> 2;                         // query half (accumulator) this warp drains
+    const int q = q0 + hf * kSimHalf + qd * 32 + lane;
+    const bool active = hf < nhalf;
+    const bool qok = active && q < Nq;
+    const float c2 = inv_tau * 1.4426950408889634f;   // exp(x/tau) = exp2(x * c2)
+    float m = -INFINITY, ssum = 0.f;               // running max of raw S and sum exp2((S - m) c2)
     const bool vec_ok = (Nr % 4 == 0) && ((((uintptr_t)S) & 15) == 0);
     int i = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
       mbar_wait(&tail->acc_full[buf], (i >> 1) & 1);
       tc_fence_after();
-      const int r0 = t * kSimBN;
-      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * kSimBN);
-      for (int col = 0; col < kSimBN; col += 16) {
-        if (r0 + col >= Nr) break;                 // warp-uniform: whole chunk out of range
-        uint32_t v[16];
-        tmem_ld_16(taddr + (uint32_t)col, v);
-        tmem_ld_wait();
-        const int nval = min(16, Nr - (r0 + col));
-        if (S && qok) {
-          float* dst = S + (long long)q * Nr + r0 + col;
-          if (vec_ok && nval == 16) {
+      if (active) {
+        const int r0 = t * kSimBN;
+        const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)((buf * 2 + hf) * kSimBN);
+        for (int col = 0; col < kSimBN; col += 32) {
+          if (r0 + col >= Nr) break;               // warp-uniform: whole chunk out of range
+          uint32_t v[32];
+          tmem_ld_32(taddr + (uint32_t)col, v);
+          tmem_ld_wait();
+          const int nval = min(32, Nr - (r0 + col));
+          if (S && qok) {
+            float* dst = S + (long long)q * Nr + r0 + col;
+            if (vec_ok && nval == 32) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          } else {
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (j < nval) dst[j] = __uint_as_float(v[j]);
+              for (int j = 0; j < 32; ++j)
+                if (j < nval) dst[j] = __uint_as_float(v[j]);
+            }
           }
-        }
-        if (part) {
-          float cm = -INFINITY;
+          if (part) {
+            if (nval == 32) {
+              // full chunk: max tree, then 4 independent exp2/add chains (1 FFMA + 1 MUFU + 1 FADD per element)
+              float t8[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nval) cm = fmaxf(cm, __uint_as_float(v[j]) * inv_tau);
-          if (cm > m) { ssum *= __expf(m - cm); m = cm; }
+              for (int j = 0; j < 8; ++j)
+                t8[j] = fmaxf(fmaxf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                              fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+              const float cm = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
+              if (cm > m) { ssum *= ex2_approx((m - cm) * c2); m = cm; }
+              const float mc = m * c2;
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < nval) ssum += __expf(__uint_as_float(v[j]) * inv_tau - m);
+              for (int j = 0; j < 8; ++j) {
+                a0 += ex2_approx(fmaf(__uint_as_float(v[4 * j]), c2, -mc));
+                a1 += ex2_approx(fmaf(__uint_as_float(v[4 * j + 1]), c2, -mc));
+                a2 += ex2_approx(fmaf(__uint_as_float(v[4 * j + 2]), c2, -mc));
+                a3 += ex2_approx(fmaf(__uint_as_float(v[4 * j + 3]), c2, -mc));
+              }
+              ssum += (a0 + a1) + (a2 + a3);
+            } else {
+              float cm = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nval) cm = fmaxf(cm, __uint_as_float(v[j]));
+              if (cm > m) { ssum *= ex2_approx((m - cm) * c2); m = cm; }
+              const float mc = m * c2;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nval) ssum += ex2_approx(fmaf(__uint_as_float(v[j]), c2, -mc));
+            }
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
     }
-    if (part) {
-      float* o = part + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * kSimBM + qd * 32 + lane) * 2;
-      o[0] = m;
+    if (part && active) {
+      float* o = part + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * kSimBM + hf * kSimHalf + qd * 32 + lane) * 2;
+      o[0] = m * inv_tau;     // partial max in units of S / tau, as the combine kernel expects
       o[1] = ssum;
     }
   }
@@ -162,10 +202,10 @@ using namespace cor;
 extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse,
                                 void* work, cor_stream_t stream) {
   COR_REQUIRE(regions && queries && (S || lse), "cor_sim_umma_fwd: null pointer");
-  COR_REQUIRE(Nr > 0 && Nq > 0 && D % kSimBK == 0 && D >= kSimBK && D <= 4 * kSimBK, "cor_sim_umma_fwd: need D in {64,128,192,256} (D=%d)", D);
+  COR_REQUIRE(Nr > 0 && Nq > 0 && D % kSimBK == 0 && D >= kSimBK && D <= kSimMaxKB * kSimBK, "cor_sim_umma_fwd: need D in {64,128,192,256} (D=%d)", D);
   COR_REQUIRE(!lse || work, "cor_sim_umma_fwd: lse needs a work buffer");
   CUtensorMap tmQ, tmR;
-  int rc = umma::encode_tmap_bf16_2d(&tmQ, queries, (uint64_t)Nq, (uint64_t)D, kSimBM, kSimBK);
+  int rc = umma::encode_tmap_bf16_2d(&tmQ, queries, (uint64_t)Nq, (uint64_t)D, kSimHalf, kSimBK);
   if (rc) return rc;
   rc = umma::encode_tmap_bf16_2d(&tmR, regions, (uint64_t)Nr, (uint64_t)D, kSimBN, kSimBK);
   if (rc) return rc;
@@ -173,13 +213,13 @@ extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr
   int gx = sm_count() / qtiles;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
-  const size_t smem = (size_t)4 * kSimABytes + (size_t)kSimStages * kSimBBytes + sizeof(SimSmemTail) + 1024;
+  const size_t smem = (size_t)2 * kSimMaxKB * kSimABytes + (size_t)kSimStages * kSimBBytes + sizeof(SimSmemTail) + 1024;
   cudaStream_t st = as_stream(stream);
   COR_CUDA(cudaFuncSetAttribute(sim_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* part = lse ? (float*)work : nullptr;
-  sim_umma_kernel<<<dim3(gx, qtiles), 192, smem, st>>>(tmQ, tmR, Nr, Nq, D / kSimBK, inv_tau, S, part);
+  sim_umma_kernel<<<dim3(gx, qtiles), 320, smem, st>>>(tmQ, tmR, Nr, Nq, D / kSimBK, inv_tau, S, part);
   rc = check_launch("sim_umma_kernel");
   if (rc || !lse) return rc;
-  // same combine kernel as the streaming producer: [qtile][nparts][qt][2]
+  // inactive query rows of a half-empty last tile publish nothing; the combine only reads rows < Nq
   return launch_lse_combine(part, Nq, gx, kSimBM, lse, st);
 }

@@ -28,6 +28,27 @@ __device__ __forceinline__ float upsampled_sigmoid(const TP* __restrict__ p, int
   return sigmoid_acc(z);
 }
 
+// All threads of the block reduce the per-chunk (min,max) partials of one sample (a serial loop in one
+// thread would put ~chunks L2 round trips in front of every CTA).
+__device__ __forceinline__ void block_minmax(const float* __restrict__ part, int chunks, float& s_mn, float& s_mx) {
+  __shared__ float wmn[32], wmx[32];
+  float mn = INFINITY, mx = -INFINITY;
+  for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+    mn = fminf(mn, part[2 * c]);
+    mx = fmaxf(mx, part[2 * c + 1]);
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { wmn[threadIdx.x >> 5] = mn; wmx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 1; w < nw; ++w) { mn = fminf(mn, wmn[w]); mx = fmaxf(mx, wmx[w]); }
+    s_mn = mn; s_mx = mx;
+  }
+  __syncthreads();
+}
+
 // grid = (chunks, N); minmax_part [N][chunks][2]
 template <typename TP>
 __global__ void __launch_bounds__(256) val_minmax_kernel(const TP* __restrict__ pred, int H, int W, int Ho, int Wo,
@@ -64,15 +85,7 @@ __global__ void __launch_bounds__(256) val_write_kernel(const TP* __restrict__ p
   __shared__ double scratch[4 * 32];
   __shared__ float s_mn, s_mx;
   const int n = blockIdx.y;
-  if (threadIdx.x == 0) {
-    float mn = INFINITY, mx = -INFINITY;
-    for (int c = 0; c < chunks; ++c) {
-      mn = fminf(mn, mm_part[((long long)n * chunks + c) * 2]);
-      mx = fmaxf(mx, mm_part[((long long)n * chunks + c) * 2 + 1]);
-    }
-    s_mn = mn; s_mx = mx;
-  }
-  __syncthreads();
+  block_minmax(mm_part + (long long)n * chunks * 2, chunks, s_mn, s_mx);
   const float mn = s_mn, den = s_mx - s_mn + 1e-8f;
   const TP* p = pred + (long long)n * H * W;
   const float sh = (float)H / (float)Ho, sw = (float)W / (float)Wo;
@@ -117,6 +130,108 @@ __global__ void val_metrics_kernel(const double* __restrict__ met_part, int N, i
   m[0] = (float)dice; m[1] = (float)(ad / total); m[2] = (float)iou; m[3] = (float)((dice + dice_b) / 2); m[4] = (float)((iou + iou_b) / 2);
 }
 
+// ---- exact 4x up-sampling fast path (the shipped 256^2 -> 1024^2 case) ------------------------------------
+// For an integer factor 4 the align_corners=False source coordinate of output 4*sx+j is sx + (j+.5)/4 - .5:
+// outputs j=0,1 blend source columns (sx-1, sx) with weights (.375,.625) / (.125,.875), outputs j=2,3 blend
+// (sx, sx+1) with (.875,.125) / (.625,.375); index clamping at the borders reproduces ATen's src<0 -> 0 and
+// x1 = x0 rules exactly.  One thread turns a 3x3 source neighbourhood into a 4x4 output block: 9 loads, 16
+// results, 16-byte coalesced stores.
+// 1/(1+exp(-z)) on the SFU (MUFU.EX2 + MUFU.RCP): ~2 ulp, monotone, used for BOTH the min/max and the map
+__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
+
+template <typename TP>
+__device__ __forceinline__ void up4_block(const TP* __restrict__ p, int H, int W, int sy, int sx, float (&o)[4][4]) {
+  const int ym = max(sy - 1, 0), yp = min(sy + 1, H - 1), xm = max(sx - 1, 0), xp = min(sx + 1, W - 1);
+  const int ys[3] = {ym, sy, yp};
+  float hrow[3][4];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const TP* q = p + (long long)ys[r] * W;
+    const float a = to_f<TP>(__ldg(q + xm)), b = to_f<TP>(__ldg(q + sx)), c = to_f<TP>(__ldg(q + xp));
+    hrow[r][0] = 0.625f * b + 0.375f * a;     // lambda0 * v[x0] + lambda1 * v[x1] with x0 = sx-1: (1-.625)*a + .625*b
+    hrow[r][1] = 0.875f * b + 0.125f * a;
+    hrow[r][2] = 0.875f * b + 0.125f * c;
+    hrow[r][3] = 0.625f * b + 0.375f * c;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    o[0][j] = 0.625f * hrow[1][j] + 0.375f * hrow[0][j];
+    o[1][j] = 0.875f * hrow[1][j] + 0.125f * hrow[0][j];
+    o[2][j] = 0.875f * hrow[1][j] + 0.125f * hrow[2][j];
+    o[3][j] = 0.625f * hrow[1][j] + 0.375f * hrow[2][j];
+  }
+}
+
+template <typename TP>
+__global__ void __launch_bounds__(256) val_up4_minmax_kernel(const TP* __restrict__ pred, int H, int W, float* __restrict__ part) {
+  __shared__ float smn[8], smx[8];
+  const int n = blockIdx.y;
+  const TP* p = pred + (long long)n * H * W;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    float o[4][4];
+    up4_block<TP>(p, H, W, i / W, i % W, o);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { mn = fminf(mn, o[a][b]); mx = fmaxf(mx, o[a][b]); }
+  }
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, smn[w]); mx = fmaxf(mx, smx[w]); }
+    float* o = part + ((long long)n * gridDim.x + blockIdx.x) * 2;
+    // sigmoid is monotone: min / max of sigmoid(z) are sigmoid(min z) / sigmoid(max z)
+    o[0] = sigmoid_fast(mn); o[1] = sigmoid_fast(mx);
+  }
+}
+
+template <typename TP, typename TG>
+__global__ void __launch_bounds__(256) val_up4_write_kernel(const TP* __restrict__ pred, int H, int W, const float* __restrict__ mm_part,
+                                                            int chunks, float* __restrict__ post, uint8_t* __restrict__ hard,
+                                                            const TG* __restrict__ gt, float gscale, double* __restrict__ met_part) {
+  __shared__ double scratch[4 * 32];
+  __shared__ float s_mn, s_mx;
+  const int n = blockIdx.y;
+  block_minmax(mm_part + (long long)n * chunks * 2, chunks, s_mn, s_mx);
+  const float mn = s_mn, inv_den = 1.f / (s_mx - s_mn + 1e-8f);
+  const TP* p = pred + (long long)n * H * W;
+  const int Wo = 4 * W;
+  const long long obase = (long long)n * 16 * H * W;
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int sy = i / W, sx = i % W;
+    float o[4][4];
+    up4_block<TP>(p, H, W, sy, sx, o);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float v[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[b] = (sigmoid_fast(o[a][b]) - mn) * inv_den;
+      const long long off = obase + (long long)(4 * sy + a) * Wo + 4 * sx;
+      if (post) *reinterpret_cast<float4*>(post + off) = make_float4(v[0], v[1], v[2], v[3]);
+      if (hard) *reinterpret_cast<uchar4*>(hard + off) = make_uchar4(v[0] > 0.5f ? 255 : 0, v[1] > 0.5f ? 255 : 0, v[2] > 0.5f ? 255 : 0, v[3] > 0.5f ? 255 : 0);
+      if (gt) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const float g = to_f<TG>(gt[off + b]) * gscale;
+          f0 = fmaf(v[b], g, f0); f1 += v[b]; f2 += g; f3 += fabsf(v[b] - g);
+        }
+      }
+    }
+  }
+  if (gt) {
+    double acc[4] = {f0, f1, f2, f3};
+    block_sum<4>(acc, scratch);
+    if (threadIdx.x == 0) {
+      double* o = met_part + ((long long)n * gridDim.x + blockIdx.x) * 4;
+      o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+    }
+  }
+}
+
 static int val_chunks(int N, long long total) {
   long long c = ((long long)sm_count() * 8 + N - 1) / N;
   const long long cap = (total + 1023) / 1024;
@@ -146,6 +261,28 @@ extern "C" int cor_val_post(const void* pred, int pred_dtype, int N, int H, int 
   double* met_part = reinterpret_cast<double*>(work);
   float* mm_part = reinterpret_cast<float*>(met_part + (size_t)N * 1024 * 4);
   dim3 grid(chunks, N);
+  const bool up4 = Ho == 4 * H && Wo == 4 * W && (!post || (((uintptr_t)post) & 15) == 0) && (!hard || (((uintptr_t)hard) & 3) == 0);
+  if (up4) {
+    int c4 = ceil_div((long long)H * W, 256);
+    if (c4 > 1024) c4 = 1024;
+    dim3 g4(c4, N);
+    if (pred_dtype == COR_F32) val_up4_minmax_kernel<float><<<g4, 256, 0, st>>>((const float*)pred, H, W, mm_part);
+    else if (pred_dtype == COR_BF16) val_up4_minmax_kernel<bf16><<<g4, 256, 0, st>>>((const bf16*)pred, H, W, mm_part);
+    else COR_REQUIRE(false, "cor_val_post: unsupported pred dtype %d", pred_dtype);
+    int rc4 = check_launch("val_up4_minmax_kernel");
+    if (rc4) return rc4;
+#define COR_VW4(TP, TG) val_up4_write_kernel<TP, TG><<<g4, 256, 0, st>>>((const TP*)pred, H, W, mm_part, c4, post, hard, (const TG*)gt, gt_scale, met_part)
+    if (pred_dtype == COR_F32 && (!gt || gt_dtype == COR_F32)) COR_VW4(float, float);
+    else if (pred_dtype == COR_BF16 && (!gt || gt_dtype == COR_F32)) COR_VW4(bf16, float);
+    else if (pred_dtype == COR_F32 && gt_dtype == COR_U8) COR_VW4(float, uint8_t);
+    else if (pred_dtype == COR_BF16 && gt_dtype == COR_U8) COR_VW4(bf16, uint8_t);
+    else COR_REQUIRE(false, "cor_val_post: unsupported gt dtype %d", gt_dtype);
+#undef COR_VW4
+    rc4 = check_launch("val_up4_write_kernel");
+    if (rc4 || !gt) return rc4;
+    val_metrics_kernel<<<ceil_div(N, 128), 128, 0, st>>>(met_part, N, c4, (double)total, metrics);
+    return check_launch("val_metrics_kernel");
+  }
   if (pred_dtype == COR_F32) val_minmax_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, H, W, Ho, Wo, mm_part);
   else if (pred_dtype == COR_BF16) val_minmax_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)pred, H, W, Ho, Wo, mm_part);
   else COR_REQUIRE(false, "cor_val_post: unsupported pred dtype %d", pred_dtype);

@@ -28,7 +28,7 @@ LAUNCHES = {"count": 0}
 _KERNELS_PER_CALL = {
     "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 1, "cor_rows_finalize": 1,
     "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_umma": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
-    "cor_fgbg_loss_bwd": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
+    "cor_fgbg_loss_bwd": 1, "cor_step_combine": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
     "cor_sim_umma_fwd": 2, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
     "cor_val_post": 3,
 }
@@ -282,15 +282,13 @@ class _FgBgFn(torch.autograd.Function):
         n, Cc = fg_rows.shape
         fg_c = _rows2d(fg_rows)
         bg_c = _rows2d(bg_rows) if bg_rows is not None else None
-        if bg_c is not None and bg_c.stride(0) != fg_c.stride(0):
-            fg_c, bg_c = fg_c.contiguous(), bg_c.contiguous()
         comb_c = _rows2d(comb)
         stats_c = _rows2d(stats)
         lib = L.load()
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
         aux = torch.empty(lib.cor_fgbg_aux_floats(n, Cc), dtype=torch.float32, device=dev)
-        _call("cor_fgbg_loss_fwd", dev, ptr(fg_c), ptr(bg_c), _ll(fg_c.stride(0)), ptr(comb_c), _ll(comb_c.stride(0)), ptr(stats_c),
-              _ll(stats_c.stride(0)), n, Cc, int(bg_mode), ptr(out4), ptr(aux))
+        _call("cor_fgbg_loss_fwd", dev, ptr(fg_c), _ll(fg_c.stride(0)), ptr(bg_c), _ll(bg_c.stride(0) if bg_c is not None else 0),
+              ptr(comb_c), _ll(comb_c.stride(0)), ptr(stats_c), _ll(stats_c.stride(0)), n, Cc, int(bg_mode), ptr(out4), ptr(aux))
         ctx.save_for_backward(fg_c, bg_c, comb_c, out4, aux)
         ctx.bg_mode = int(bg_mode)
         ctx.comb_dtype = comb.dtype
@@ -306,8 +304,9 @@ class _FgBgFn(torch.autograd.Function):
         g_fg = torch.empty((n, Cc), dtype=torch.float32, device=dev)
         g_bg = torch.empty((n, Cc), dtype=torch.float32, device=dev) if bg_c is not None else None
         g_comb = torch.empty((n, Cc), dtype=torch.float32, device=dev)
-        _call("cor_fgbg_loss_bwd", dev, ptr(fg_c), ptr(bg_c), _ll(fg_c.stride(0)), ptr(comb_c), _ll(comb_c.stride(0)), n, Cc,
-              ctx.bg_mode, ptr(out4), ptr(aux), ptr(g2), ptr(g_fg), ptr(g_bg), ptr(g_comb))
+        _call("cor_fgbg_loss_bwd", dev, ptr(fg_c), _ll(fg_c.stride(0)), ptr(bg_c), _ll(bg_c.stride(0) if bg_c is not None else 0),
+              ptr(comb_c), _ll(comb_c.stride(0)), n, Cc, ctx.bg_mode, ptr(out4), ptr(aux), ptr(g2), ptr(g_fg), _ll(Cc), 0, ptr(g_bg),
+              _ll(Cc), ptr(g_comb), _ll(Cc), 0)
         return g_fg, g_bg, g_comb.view(ctx.comb_shape).to(ctx.comb_dtype), None, None
 
 
@@ -328,12 +327,16 @@ class _SegLossFn(torch.autograd.Function):
         pred_c = _as_supported_float(pred)
         if mask.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
             mask = mask.float()
-        mask_c = mask.contiguous()
-        if pred_c.dim() != 4 or mask_c.dim() != 4 or pred_c.shape[:2] != mask_c.shape[:2]:
+        if pred_c.dim() != 4 or mask.dim() != 4 or pred_c.shape[:2] != mask.shape[:2]:
             raise CorError(f"seg_loss: pred {tuple(pred.shape)} and mask {tuple(mask.shape)} must be [N,C,H,W] with equal N,C")
+        Hm, Wm = mask.shape[2:]
+        # a [N,1,H,W] slice of a larger [N,M,H,W] tensor is read in place through its sample stride (no copy)
+        if mask.shape[1] == 1 and mask.stride(3) == 1 and mask.stride(2) == Wm and mask.stride(0) >= Hm * Wm:
+            mask_c, nstride = mask, mask.stride(0)
+        else:
+            mask_c, nstride = mask.contiguous(), Hm * Wm
         N = pred_c.shape[0] * pred_c.shape[1]
         H, W = pred_c.shape[2:]
-        Hm, Wm = mask_c.shape[2:]
         lib = L.load()
         out8 = torch.empty(8, dtype=torch.float32, device=dev)
         per = torch.empty((N, 8), dtype=torch.float32, device=dev)
@@ -342,8 +345,8 @@ class _SegLossFn(torch.autograd.Function):
         w_save = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need else None
         work = _work(lib.cor_seg_loss_work_bytes(N, H, W), dev)
         _call("cor_seg_loss_fwd", dev, ptr(pred_c), dtype_code(pred_c), ptr(mask_c), dtype_code(mask_c),
-              _f(_mask_scale(mask_c, mask_scale)), N, H, W, Hm, Wm, _f(w1), _f(w2), _f(focal_alpha), _f(focal_gamma), _f(dice_smooth),
-              ptr(out8), ptr(per), ptr(t_save), ptr(w_save), ptr(work))
+              _f(_mask_scale(mask_c, mask_scale)), N, H, W, Hm, Wm, _ll(nstride), _f(w1), _f(w2), _f(focal_alpha), _f(focal_gamma),
+              _f(dice_smooth), ptr(out8), ptr(per), ptr(t_save), ptr(w_save), ptr(work))
         ctx.save_for_backward(pred_c, t_save, w_save, per)
         ctx.cfg = (N, H, W, float(w1), float(w2), pred.dtype)
         return out8[0].clone(), out8.clone()
@@ -365,8 +368,9 @@ def seg_loss(pred: torch.Tensor, mask: torch.Tensor, w1: float = 1.0, w2: float 
     """Weighted BCE + weighted IoU (loss_func.py:5-32); ``mask`` may be at any resolution -- it is
     bilinearly resampled to the logit grid inside the kernel (trainer_v3_g.py:67).  With
     ``return_extras`` also returns the 8-vector {loss, dice, focal, mean wbce, mean wiou, ...}."""
-    loss, extra = _SegLossFn.apply(pred, mask, float(w1), float(w2), mask_scale, float(focal_alpha), float(focal_gamma),
-                                   float(dice_smooth))
+    # the focal term (a powf per pixel) is only evaluated when the extras are asked for
+    loss, extra = _SegLossFn.apply(pred, mask, float(w1), float(w2), mask_scale, float(focal_alpha),
+                                   float(focal_gamma) if return_extras else -1.0, float(dice_smooth))
     return (loss, extra) if return_extras else loss
 
 

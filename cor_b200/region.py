@@ -67,9 +67,155 @@ class RegionStepOut:
     regions: torch.Tensor          # [B, M, C] unit rows (detached view for retrieval)
 
 
+class _FusedStepFn(torch.autograd.Function):
+    """The whole region path as ONE autograd node: every kernel of the forward is launched back to
+    back on the current stream, the backward is written out by hand, and no tensor glue (slices,
+    zeros + scatter, tiny adds) sits between them.  Used by :func:`region_step` when the tensor-core
+    pooling engine applies; the modular ops remain the general path."""
+
+    @staticmethod
+    def forward(ctx, pred, emb, comb, masks, tau, nce_weight, gather, sim_engine, bg_mode, w_fg, w_bg):
+        from . import _lib as L
+        ptr, _f, _ll, call = ops.ptr, ops._f, ops._ll, ops._call
+        dev = L.require_cuda(pred, emb, comb, masks)
+        lib = L.load()
+        B, M = masks.shape[:2]
+        Cc, h, w = emb.shape[1:]
+        P = h * w
+        emb_c = emb.contiguous()
+        pred_c = ops._as_supported_float(pred)
+        comb_c = comb.reshape(B, -1).float().contiguous()
+        f32 = dict(dtype=torch.float32, device=dev)
+        need_emb = emb.requires_grad
+        # 1. masks -> bf16 weights (+ raw fp32 weights for the backward) + full-resolution stats
+        Rp = (M + 1 + 15) // 16 * 16
+        w16 = ops._umma_weight_buffer(dev, B, Rp, M, P)
+        w32, stats = ops.mask_prep(masks.reshape(B * M, *masks.shape[2:]), (h, w), ops.W_CLAMP, want_f32=need_emb, bf16_out=w16,
+                                   group=M, group_stride=Rp * P)
+        # 2. pooling GEMM (split-K partials), 3. row epilogues: all fg rows, bg rows of the GT masks only
+        ks = lib.cor_pool_umma_ksplit(B, Cc, P)
+        part = torch.empty((ks, B, Rp, Cc), **f32)
+        call("cor_pool_umma_fwd", dev, ptr(emb_c), ptr(w16), B, Cc, P, Rp, ptr(part))
+        fg = torch.empty((B * M, Cc), **f32)
+        fg16 = torch.empty((B * M, Cc), dtype=torch.bfloat16, device=dev)
+        inv_fg = torch.empty((B * M,), **f32)
+        split = B * Rp * Cc
+        call("cor_rows_finalize", dev, ptr(part), M, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, 3:]), 4, _f(1e-8), B * M, Cc, 1, 1,
+             None, _f(0.0), ptr(fg), ptr(fg16), ptr(inv_fg))
+        bg = torch.empty((B, Cc), **f32)
+        inv_bg = torch.empty((B,), **f32)
+        call("cor_rows_finalize", dev, ptr(part), 1, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, 3:]), 4 * M, _f(1e-8), B, Cc, 1, 1,
+             ptr(part[0, :, M, :]), _f(float(P)), ptr(bg), None, ptr(inv_bg))
+        # 4. fg / bg cosine losses on the GT rows (row b*M of fg, row b of bg)
+        out4 = torch.empty(4, **f32)
+        aux = torch.empty(lib.cor_fgbg_aux_floats(B, Cc), **f32)
+        call("cor_fgbg_loss_fwd", dev, ptr(fg), _ll(M * Cc), ptr(bg), _ll(Cc), ptr(comb_c), _ll(Cc), ptr(stats), _ll(4 * M), B, Cc,
+             int(bg_mode), ptr(out4), ptr(aux))
+        # 5. segmentation loss against the GT mask, resample fused
+        gt = masks[:, 0]                       # [B,Hm,Wm] view; read in place through its sample stride
+        Hm, Wm = gt.shape[1:]
+        if not (gt.stride(2) == 1 and gt.stride(1) == Wm):
+            gt = gt.contiguous()
+        N = B
+        H, W = pred_c.shape[2:]
+        out8 = torch.empty(8, **f32)
+        per = torch.empty((N, 8), **f32)
+        need_pred = pred.requires_grad
+        t_save = torch.empty((N, H, W), **f32) if need_pred else None
+        w_save = torch.empty((N, H, W), **f32) if need_pred else None
+        work = ops._work(lib.cor_seg_loss_work_bytes(N, H, W), dev)
+        call("cor_seg_loss_fwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(gt), L.dtype_code(gt), _f(ops._mask_scale(gt, None)), N, H, W,
+             Hm, Wm, _ll(gt.stride(0)), _f(1.0), _f(1.0), _f(0.25), _f(-1.0), _f(1.0), ptr(out8), ptr(per), ptr(t_save), ptr(w_save),
+             ptr(work))
+        # 6. InfoNCE of every composed query against all (gathered) regions
+        q16 = comb_c.to(torch.bfloat16)
+        rank, ws = cdist.world()
+        n_local = B * M
+        if gather and ws > 1:
+            r16 = torch.empty((ws * n_local, Cc), dtype=torch.bfloat16, device=dev)
+            torch.distributed.all_gather_into_tensor(r16, fg16)
+            offset = rank * n_local
+        else:
+            r16, offset, ws = fg16, 0, 1
+        targets = torch.arange(B, device=dev, dtype=torch.int64) * M + offset
+        inv_tau = 1.0 / float(tau)
+        _, lse = ops._sim_forward(r16, q16, inv_tau, False, True, sim_engine)
+        nce = torch.empty(1, **f32)
+        tgt = torch.empty((B,), **f32)
+        call("cor_infonce_fwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), r16.shape[0], B, Cc, _f(inv_tau), ptr(nce), ptr(tgt))
+        loss = torch.empty(1, **f32)
+        call("cor_step_combine", dev, ptr(out8), ptr(out4), ptr(nce), _f(w_fg), _f(w_bg), _f(nce_weight), ptr(loss))
+        ctx.save_for_backward(pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32)
+        ctx.cfg = (B, M, Cc, h, w, float(inv_tau), float(nce_weight), int(bg_mode), float(w_fg), float(w_bg), ws, offset, n_local,
+                   pred.dtype, emb.dtype, comb.dtype, tuple(comb.shape), need_pred, need_emb, comb.requires_grad)
+        ctx.mark_non_differentiable(fg, out8, out4, nce)
+        return loss[0], out8, out4, nce, fg
+
+    @staticmethod
+    def backward(ctx, g_loss, *_unused):
+        from . import _lib as L
+        ptr, _f, _ll, call = ops.ptr, ops._f, ops._ll, ops._call
+        (pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32) = ctx.saved_tensors
+        (B, M, Cc, h, w, inv_tau, nce_weight, bg_mode, w_fg, w_bg, ws, offset, n_local, pred_dt, emb_dt, comb_dt, comb_shape,
+         need_pred, need_emb, need_comb) = ctx.cfg
+        dev = fg.device
+        lib = L.load()
+        P = h * w
+        f32 = dict(dtype=torch.float32, device=dev)
+        g = g_loss.reshape(1).float().contiguous()
+        g_pred = g_emb = g_comb = None
+        if need_pred:
+            N, H, W = t_save.shape
+            g_pred = torch.empty_like(pred_c)
+            call("cor_seg_loss_bwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _f(1.0), _f(1.0),
+                 ptr(g), ptr(g_pred), L.dtype_code(g_pred))
+            g_pred = g_pred.to(pred_dt)
+        # InfoNCE backward first: it WRITES g_regions (all gathered rows) and g_queries ...
+        Nr = r16.shape[0]
+        g_regions = torch.empty((Nr, Cc), **f32)
+        g_q = torch.empty((B, Cc), **f32)
+        work = ops._work(lib.cor_sim_work_bytes(B, Nr, Cc), dev)
+        g_nce = g * nce_weight
+        call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), ptr(g_regions),
+             ptr(g_q), ptr(work))
+        if ws > 1:
+            local = torch.empty((n_local, Cc), **f32)
+            torch.distributed.reduce_scatter_tensor(local, g_regions, op=torch.distributed.ReduceOp.SUM)
+            g_regions = local
+        # ... then the fg/bg backward ADDS its GT-row gradients into g_regions (row b*M) and g_queries
+        g2 = torch.cat([g * w_fg, g * w_bg])
+        g_bg = torch.empty((B, Cc), **f32) if bg_mode == 1 else None
+        call("cor_fgbg_loss_bwd", dev, ptr(fg), _ll(M * Cc), ptr(bg), _ll(Cc), ptr(comb_c), _ll(Cc), B, Cc, bg_mode, ptr(out4), ptr(aux),
+             ptr(g2), ptr(g_regions), _ll(M * Cc), 1, ptr(g_bg), _ll(Cc), ptr(g_q), _ll(Cc), 1)
+        if need_comb:
+            g_comb = g_q.view(comb_shape).to(comb_dt)
+        if need_emb:
+            gs_fg = torch.empty((B * M, Cc), **f32)
+            call("cor_rows_finalize_bwd", dev, ptr(g_regions), ptr(fg), ptr(inv_fg), ptr(stats[:, 3:]), 4, _f(1e-8), B * M, Cc, 1, 1, 0,
+                 _f(0.0), ptr(gs_fg))
+            gs_bg_full = None
+            if g_bg is not None:          # paired bg mode: background gradient lives on the GT rows only
+                gs_bg = torch.empty((B, Cc), **f32)
+                call("cor_rows_finalize_bwd", dev, ptr(g_bg), ptr(bg), ptr(inv_bg), ptr(stats[:, 3:]), 4 * M, _f(1e-8), B, Cc, 1, 1, 1,
+                     _f(float(P)), ptr(gs_bg))
+                gs_bg_full = torch.zeros((B, M, Cc), **f32)
+                gs_bg_full[:, 0, :] = gs_bg
+            g_emb_c = torch.empty((B, Cc, h, w), dtype=emb_dt if emb_dt in (torch.float32, torch.bfloat16) else torch.float32, device=dev)
+            name = "cor_pool_bwd_umma" if lib.cor_pool_bwd_umma_ok(B, Cc, P, M, int(gs_bg_full is not None)) else "cor_pool_bwd_feat"
+            call(name, dev, ptr(gs_fg), ptr(gs_bg_full), ptr(w32), _ll(P), B, Cc, P, M, ops.W_CLAMP, ptr(g_emb_c), L._DTYPES[g_emb_c.dtype])
+            g_emb = g_emb_c.to(emb_dt)
+        return g_pred, g_emb, g_comb, None, None, None, None, None, None, None, None
+
+
+def _fused_ok(emb, masks, pool_engine):
+    B, M = masks.shape[:2]
+    P = emb.shape[2] * emb.shape[3]
+    return pool_engine in ("auto", "umma") and ops.umma_pool_eligible(emb, M, P, ops.W_CLAMP, 1) and emb.shape[1] % 8 == 0
+
+
 def region_step(pred: torch.Tensor, emb: torch.Tensor, comb: torch.Tensor, masks: torch.Tensor, *, tau: float = 0.07,
                 nce_weight: float = 1.0, gather: bool = True, pool_engine: str = "auto", sim_engine: str = "auto",
-                bg_mode: int = 0) -> RegionStepOut:
+                bg_mode: int = 0, fused: bool = True) -> RegionStepOut:
     """One forward of the whole region path for a batch of triplets with M candidate masks each
     (mask 0 of every image is the ground-truth ``query_mask``):
 
@@ -78,11 +224,17 @@ def region_step(pred: torch.Tensor, emb: torch.Tensor, comb: torch.Tensor, masks
         nce  = InfoNCE(comb_b vs all B*M (x world) pooled regions, target = region (b,0))   [Class N]
         loss = seg + 5 fg + 5 bg + nce_weight * nce
 
-    ONE pass over the masks and ONE pass over the feature map serve fg, bg and all M regions.
+    ONE pass over the masks and ONE pass over the feature map serve fg, bg and all M regions.  With bf16
+    features and >= 16 masks the step runs as a single fused autograd node (tensor-core pooling, hand
+    written backward); other shapes compose the modular ops.
     """
     B, M = masks.shape[:2]
     if comb.shape[0] != B or emb.shape[0] != B or pred.shape[0] != B:
         raise CorError("region_step: batch sizes differ")
+    if fused and _fused_ok(emb, masks, pool_engine) and pred.dim() == 4 and pred.shape[1] == 1:
+        loss, out8, out4, nce, fg = _FusedStepFn.apply(pred, emb, comb, masks, float(tau), float(nce_weight), bool(gather), sim_engine,
+                                                       int(bg_mode), 5.0, 5.0)
+        return RegionStepOut(loss=loss, seg=out8[0], fg=out4[0], bg=out4[1], nce=nce[0], regions=fg.view(B, M, -1))
     pool = ops.region_pool(emb, masks, transform=ops.W_CLAMP, normalize=True, pair=True, engine=pool_engine, want_bf16=True)
     Cc = pool.fg.shape[-1]
     q = comb.reshape(B, -1)

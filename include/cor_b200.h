@@ -130,12 +130,19 @@ int cor_pool_bwd_maps(const void* feat, int feat_dtype, const float* maps, long 
  * Backward writes g_fg_rows, g_bg_rows [n, C] and g_comb [n, C] for upstream scalars g[0], g[1]
  * (device pointer to 2 floats). */
 size_t cor_fgbg_aux_floats(int n, int C);   /* floats of `aux` scratch kept from forward to backward */
-int cor_fgbg_loss_fwd(const float* fg_rows, const float* bg_rows, long long row_stride, const float* comb,
-                      long long comb_stride, const float* stats, long long stats_stride, int n, int C,
-                      int bg_mode, float* out4, float* aux, cor_stream_t stream);
-int cor_fgbg_loss_bwd(const float* fg_rows, const float* bg_rows, long long row_stride, const float* comb,
-                      long long comb_stride, int n, int C, int bg_mode, const float* out4, const float* aux,
-                      const float* g2, float* g_fg_rows, float* g_bg_rows, float* g_comb, cor_stream_t stream);
+int cor_fgbg_loss_fwd(const float* fg_rows, long long fg_stride, const float* bg_rows, long long bg_stride,
+                      const float* comb, long long comb_stride, const float* stats, long long stats_stride,
+                      int n, int C, int bg_mode, float* out4, float* aux, cor_stream_t stream);
+/* g_fg_rows / g_comb are written (or, with *_accumulate, added to) at the given row strides, so a caller
+ * can fold these gradients straight into larger gradient buffers. */
+int cor_fgbg_loss_bwd(const float* fg_rows, long long fg_stride, const float* bg_rows, long long bg_stride,
+                      const float* comb, long long comb_stride, int n, int C, int bg_mode, const float* out4,
+                      const float* aux, const float* g2, float* g_fg_rows, long long gfg_stride, int fg_accumulate,
+                      float* g_bg_rows, long long gbg_stride, float* g_comb, long long gcomb_stride,
+                      int comb_accumulate, cor_stream_t stream);
+/* loss = seg[0] + w_fg * fgbg[0] + w_bg * fgbg[1] + w_nce * nce[0]   (utils/trainer_v3_g.py:67-73; nce may be NULL) */
+int cor_step_combine(const float* seg, const float* fgbg, const float* nce, float w_fg, float w_bg, float w_nce,
+                     float* loss, cor_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Segmentation loss (loss_func.py:5-32) with the target resample of trainer_v3_g.py:67 fused in.
@@ -145,7 +152,7 @@ int cor_fgbg_loss_bwd(const float* fg_rows, const float* bg_rows, long long row_
  * ---------------------------------------------------------------------------------------- */
 size_t cor_seg_loss_work_bytes(int N, int H, int W);
 int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* mask, int mask_dtype, float mask_scale,
-                     int N, int H, int W, int Hm, int Wm, float w1, float w2, float focal_alpha,
+                     int N, int H, int W, int Hm, int Wm, long long mask_nstride /* elements between samples; <=0: Hm*Wm */, float w1, float w2, float focal_alpha,
                      float focal_gamma, float dice_smooth, float* out8, float* per_sample, float* t_save,
                      float* w_save, void* work, cor_stream_t stream);
 int cor_seg_loss_bwd(const void* pred, int pred_dtype, const float* t_save, const float* w_save,

@@ -156,3 +156,27 @@ def test_pool_bwd_umma_vs_cuda_core(cfg):
     # relative Frobenius error: bf16 operand rounding only
     err = float((grads[0] - grads[1]).norm() / grads[1].norm())
     assert err < 6e-3, err
+
+
+@pytest.mark.parametrize("bg_mode", [0, 1])
+def test_fused_step_equals_modular_ops(bg_mode):
+    """region_step's single-node fused path (hand-written backward) against the composition of the
+    modular autograd ops on the same inputs: loss parts and all three gradients."""
+    from cor_b200 import region, synth
+    d = synth.make_triplets(73, B=3, M=20, C=128, h=16, w=16, H=64, W=64, hp=32, wp=32, degenerate=False)
+    d["masks"][1, 0] = 0.0                      # an invalid GT mask
+    outs = []
+    for fused in (True, False):
+        p = cu(d["pred"], grad=True)
+        c = cu(d["comb"], grad=True)
+        e = torch.from_numpy(d["emb"]).bfloat16().to(dev()).requires_grad_(True)
+        o = region.region_step(p, e, c, cu(d["masks"]), tau=0.07, gather=False, bg_mode=bg_mode, fused=fused)
+        o.loss.backward()
+        outs.append((o, p.grad.float(), c.grad.float(), e.grad.float()))
+    (a, pa, ca, ea), (b, pb, cb, eb) = outs
+    for k in ("loss", "seg", "fg", "bg", "nce"):
+        close(getattr(a, k), getattr(b, k), rtol=1e-5, atol=1e-6)
+    close(a.regions, b.regions, rtol=1e-5, atol=1e-6)
+    close(pa, pb, rtol=1e-5, atol=1e-9)
+    close(ca, cb, rtol=1e-4, atol=1e-6)
+    close(ea, eb, rtol=2e-2, atol=2e-3 * float(eb.abs().max()))
