@@ -7,6 +7,8 @@
 // HBM-bound streaming kernel: every mask byte is read exactly once with 128-bit no-allocate loads;
 // the 4 taps per output pixel hit lines the same CTA streams.  Deterministic: per-CTA partials in
 // double, reduced in fixed order by a second tiny kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cor {
@@ -162,13 +164,13 @@ __global__ void __launch_bounds__(256) mask_prep_kernel(const T* __restrict__ ma
 // +12.5 % traffic at 16x down-sampling).  A CTA owns <= kMaxRO output rows: one row-structured streaming
 // loop over its band of input rows (no synchronisation inside), ONE __syncthreads, then all threads form
 // the 4-tap samples from shared memory.  Needs rows that are whole, aligned 16-byte vectors.
-constexpr int kMaxRO = 8;          // output rows per CTA (2*kMaxRO tap rows in smem)
+constexpr int kMaxRO = 8;          // upper bound on output rows per CTA (2*max_ro tap rows in smem)
 constexpr int kSU = 4;             // independent 16-byte loads in flight per thread
 constexpr int kMaxBand = 4096;     // input rows per CTA the slot table can describe
 
 template <typename T, bool kNeedOneMinus>
-__global__ void __launch_bounds__(256) mask_prep_staged_kernel(const T* __restrict__ masks, float mscale, int Hm, int Wm, int h, int w,
-                                                               int chunks, int transform, int lanes_per_row, float* __restrict__ w_f32,
+__global__ void __launch_bounds__(256, 5) mask_prep_staged_kernel(const T* __restrict__ masks, float mscale, int Hm, int Wm, int h, int w,
+                                                               int chunks, int transform, int lanes_per_row, int max_ro, float* __restrict__ w_f32,
                                                                bf16* __restrict__ w_bf16, long long ldw, int group, long long group_stride,
                                                                double* __restrict__ part) {
   extern __shared__ uint4 tap_smem[];                 // [2*ro][vpr] vectors, then the slot table
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(256) mask_prep_staged_kernel(const T* __restri
   const int vpr = Wm / VE;
   const T* base = masks + (long long)n * Hm * Wm;
   const float sh = (float)Hm / (float)h, sw = (float)Wm / (float)w;
-  short* first_slot = reinterpret_cast<short*>(tap_smem + (size_t)2 * kMaxRO * vpr);   // [band] first slot fed by that row, or -1
+  short* first_slot = reinterpret_cast<short*>(tap_smem + (size_t)2 * max_ro * vpr);   // [band] first slot fed by that row, or -1
   __shared__ int tap_row[2 * kMaxRO];
   __shared__ float tap_l1[kMaxRO];
 
@@ -341,18 +343,19 @@ extern "C" int cor_mask_prep(const void* masks, int mask_dtype, float mask_scale
   int direct = mask_dtype == COR_F32 ? 1 : mask_dtype == COR_BF16 ? 0 : 2;
   // staged kernel: rows are whole aligned 16-byte vectors, <= kMaxRO output rows (and a describable band) per CTA
   const size_t row_bytes = (size_t)Wm * es;
-  int chunks_s = ceil_div(h, kMaxRO);
+  // measured (profiles/): 4 output rows per CTA is best for fp32/bf16 masks (5 CTAs/SM), 8 for 1-byte masks
+  const int max_ro = es == 1 ? 8 : 4;
+  int chunks_s = ceil_div(h, max_ro);
   {
     const int want = pick_chunks(n_masks, Hm, Wm, h, es);
     if (want > chunks_s) chunks_s = want;
   }
   const long long band_max = ((long long)ceil_div(h, chunks_s) * Hm + h - 1) / h + 2;
-  const size_t smem_s = (size_t)2 * kMaxRO * row_bytes + (size_t)band_max * sizeof(short) + 16;
-  // measured on B200 (profiles/): the staged kernel wins for 1-byte masks (0.24 vs 0.49 ms per GB-scale batch: the two-phase
-  // kernel is issue-bound there), while for fp32/bf16 masks the two-phase kernel's long linear streams saturate DRAM (0.72 vs
-  // 0.82 ms) even though it re-reads the tap rows.
-  const bool staged = es == 1 && (row_bytes % 16 == 0) && (((uintptr_t)masks & 15) == 0) && smem_s <= 96 * 1024 && band_max <= kMaxBand &&
-                      ceil_div(h, chunks_s) <= kMaxRO && chunks_s <= h && Hm >= h;
+  const size_t smem_s = (size_t)2 * max_ro * row_bytes + (size_t)band_max * sizeof(short) + 16;
+  // measured on B200 (profiles/): staged beats the two-phase kernel for every mask dtype (f32 0.70 vs 0.73 ms, u8 0.24 vs
+  // 0.49 ms at 1024 masks of 1024^2); COR_PREP_TWO_PHASE=1 forces the two-phase kernel for A/B runs.
+  const bool staged = !getenv("COR_PREP_TWO_PHASE") && (row_bytes % 16 == 0) && (((uintptr_t)masks & 15) == 0) && smem_s <= 96 * 1024 && band_max <= kMaxBand &&
+                      ceil_div(h, chunks_s) <= max_ro && chunks_s <= h && Hm >= h;
   int chunks = staged ? chunks_s : pick_chunks(n_masks, Hm, Wm, h, es);
   COR_REQUIRE((long long)n_masks * chunks < 2147483647LL, "cor_mask_prep: grid too large");
   dim3 grid((unsigned)(n_masks * chunks));
@@ -363,7 +366,7 @@ extern "C" int cor_mask_prep(const void* masks, int mask_dtype, float mask_scale
 #define COR_PREP_S(T_, OM_)                                                                                                   \
   do {                                                                                                                        \
     COR_CUDA(cudaFuncSetAttribute(mask_prep_staged_kernel<T_, OM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
-    mask_prep_staged_kernel<T_, OM_><<<grid, 256, smem_s, st>>>((const T_*)masks, mask_scale, Hm, Wm, h, w, chunks, transform, L, w_f32, \
+    mask_prep_staged_kernel<T_, OM_><<<grid, 256, smem_s, st>>>((const T_*)masks, mask_scale, Hm, Wm, h, w, chunks, transform, L, max_ro, w_f32, \
                                                                 (bf16*)w_bf16, ldw, group, group_stride, part);               \
   } while (0)
     if (mask_dtype == COR_F32) COR_PREP_S(float, true);
