@@ -31,7 +31,7 @@ UNIT = "triplets/s"
 CFG = dict(B=16, M=64, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, tau=0.07)
 # dram__bytes_read.sum + dram__bytes_write.sum per mask_prep_kernel launch from the committed ncu --set full capture
 # (profiles/): filled in from the capture of the SAME configuration, else null.
-TRAFFIC_NCU = {"f32": None, "u8": None}
+TRAFFIC_NCU = {"f32": 4303368320, "u8": None}   # profiles/r01_step_kernels_ncu_full_summary.csv: 4.294992 GB read + 8.376 MB written
 
 
 _T0 = time.perf_counter()
@@ -273,12 +273,13 @@ def main():
     n0 = ops.LAUNCHES["count"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()     # ncu --profile-from-start off captures only the timed region
-    with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            loss = step()
-        e1.record()
-        barrier()
+    clk = ClockSampler(local)       # samples nvidia-smi every 200 ms from here to the end of the e2e leg (GPU busy throughout)
+    clk.__enter__()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
     torch.cuda.profiler.stop()
     launches = ops.LAUNCHES["count"] - n0
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -316,6 +317,7 @@ def main():
                                       "flops": 2.0 * cfg["B"] * cfg["M"] * P * cfg["C"]}}
 
     if args.no_e2e:
+        clk.__exit__()
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": ms_step, "e2e": None,
                               "roofline": roofline, "kernel_ms_per_step": per_kernel, "gpu_launches": launches, "graphed": graphed,
@@ -348,6 +350,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = cfg["B"] * world / (float(e2e_ms) * 1e-3)
+    clk.__exit__()
 
     trace("done")
     if rank == 0:

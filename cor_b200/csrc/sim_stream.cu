@@ -306,15 +306,33 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ S, 
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned rem = sel_remaining;
-      int d = 255;
-      for (; d > 0; --d) {
-        if (hist[d] >= rem) break;
-        rem -= hist[d];
+    if (warp == 0) {
+      // digit = largest d with (count of keys whose digit > d) < remaining: warp-parallel suffix scan over
+      // the 256 bins (lane l owns bins 8l..8l+7, higher lanes = higher digits)
+      const unsigned rem = sel_remaining;
+      unsigned c[8], own = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; own += c[j]; }
+      // inclusive suffix sum of `own` over lanes
+      unsigned suf = own;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, suf, o);
+        if (lane + o < 32) suf += v;
       }
-      sel_prefix = prefix | ((unsigned)d << shift);
-      sel_remaining = rem;   // how many of the threshold-digit keys are still needed
+      const unsigned above = suf - own;                     // keys in bins of higher lanes
+      // the selected digit lies in the unique lane with above < rem <= above + own
+      const bool mine = above < rem && rem <= above + own;
+      if (mine) {
+        unsigned acc = above;
+        int d = 7;
+        for (; d > 0; --d) {
+          if (acc + c[d] >= rem) break;
+          acc += c[d];
+        }
+        sel_prefix = prefix | ((unsigned)(lane * 8 + d) << shift);
+        sel_remaining = rem - acc;   // how many of the threshold-digit keys are still needed
+      }
     }
     __syncthreads();
   }
@@ -353,17 +371,27 @@ __global__ void __launch_bounds__(256) topk_kernel(const float* __restrict__ S, 
   // 3. exact re-score (fp64 accumulation of exact bf16 products, rounded once to fp32) and sort key
   int npow = 1;
   while (npow < ncand) npow <<= 1;
-  for (int c = threadIdx.x; c < npow; c += blockDim.x) {
-    unsigned long long key = 0ull;   // padding sorts last
-    if (c < ncand) {
-      const int r = cand_idx[c];
-      double acc = 0.0;
-      for (int d = 0; d < D; ++d)
-        acc += (double)__bfloat162float(queries[(long long)q * D + d]) * (double)__bfloat162float(regions[(long long)r * D + d]);
-      const float sc = (float)acc;
-      key = ((unsigned long long)fkey(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned)r);
+  for (int c = threadIdx.x; c < npow; c += blockDim.x) cand[c] = 0ull;   // padding sorts last
+  __syncthreads();
+  // one warp per candidate: lanes take 8-element slices of the row pair, fp64 FMA, fixed-order butterfly
+  for (int c = warp; c < ncand; c += 8) {
+    const int r = cand_idx[c];
+    double acc = 0.0;
+    for (int d0 = lane * 8; d0 < D; d0 += 256) {
+      const uint4 qa = *reinterpret_cast<const uint4*>(queries + (long long)q * D + d0);
+      const uint4 ra = *reinterpret_cast<const uint4*>(regions + (long long)r * D + d0);
+      const uint32_t qw[4] = {qa.x, qa.y, qa.z, qa.w}, rw[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc += (double)bf16lo(qw[j]) * (double)bf16lo(rw[j]);
+        acc += (double)bf16hi(qw[j]) * (double)bf16hi(rw[j]);
+      }
     }
-    cand[c] = key;
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float sc = (float)acc;
+      cand[c] = ((unsigned long long)fkey(sc) << 32) | (unsigned long long)(0xffffffffu - (unsigned)r);
+    }
   }
   __syncthreads();
   // bitonic sort, descending on (score, -index)
