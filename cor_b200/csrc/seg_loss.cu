@@ -16,6 +16,8 @@ constexpr int kTH = kT + 2 * kHalo;   // 94
 constexpr int kTS = kTH + 1;      // padded row stride (odd -> conflict-free column walks)
 constexpr int kHS = kT + 1;
 constexpr int kNP = 8;            // partial sums per tile
+constexpr int kSegThreads = 512;  // 64 columns x 8 row segments of 8 rows
+constexpr int kRowsPT = kT / (kSegThreads / 64);   // rows per thread in step 3
 
 struct SegSmem {
   float t[kTH * kTS];
@@ -50,7 +52,7 @@ constexpr int kFill = 4;   // halo pixels whose taps are in flight per thread (m
 // FAST4: fp32 mask at exactly 4x the logit resolution (the shipped 1024^2 -> 256^2 case): the 2x2 taps of
 // pixel (gy,gx) are elements .y/.z of the aligned float4 at column 4*gx in rows 4*gy+1 and 4*gy+2.
 template <typename TP, typename TM, bool FAST4>
-__global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict__ pred, const TM* __restrict__ mask, float mscale, int H,
+__global__ void __launch_bounds__(kSegThreads) seg_loss_tile_kernel(const TP* __restrict__ pred, const TM* __restrict__ mask, float mscale, int H,
                                                             int W, int Hm, int Wm, long long mask_nstride, float focal_alpha, float focal_gamma,
                                                             float* __restrict__ t_save, float* __restrict__ w_save,
                                                             double* __restrict__ part) {
@@ -65,11 +67,11 @@ __global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict
   const float sh = (float)Hm / (float)H, sw = (float)Wm / (float)W;
   const TM* mbase = mask + (long long)n * mask_nstride;
 
-  // 0. prefetch this thread's 16 logits (consumed in step 3) so their latency hides behind steps 1-2
-  const int px = threadIdx.x & 63, py0 = (threadIdx.x >> 6) * 16;
-  float z[16];
+  // 0. prefetch this thread's logits (consumed in step 3) so their latency hides behind steps 1-2
+  const int px = threadIdx.x & 63, py0 = (threadIdx.x >> 6) * kRowsPT;
+  float z[kRowsPT];
 #pragma unroll
-  for (int y = 0; y < 16; ++y) {
+  for (int y = 0; y < kRowsPT; ++y) {
     const int gy = ty0 + py0 + y, gx = tx0 + px;
     z[y] = (gy < H && gx < W) ? to_f<TP>(__ldg(pred + ((long long)n * H + gy) * W + gx)) : 0.f;
   }
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict
   }
   __syncthreads();
 
-  // 3. vertical 31-sums + per-pixel terms: thread = (column, segment of 16 rows)
+  // 3. vertical 31-sums + per-pixel terms: thread = (column, segment of kRowsPT rows)
   double acc[kNP];
   {
     const int x = px, y0 = py0;
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256) seg_loss_tile_kernel(const TP* __restrict
 #pragma unroll
     for (int k = 0; k < kNP; ++k) f[k] = 0.f;
 #pragma unroll
-    for (int y = 0; y < 16; ++y) {
+    for (int y = 0; y < kRowsPT; ++y) {
       if (y > 0) s += sm.hs[(y0 + y + 30) * kHS + x] - sm.hs[(y0 + y - 1) * kHS + x];
       const int gy = ty0 + y0 + y;
       if (gy < H && gx < W) {
@@ -245,7 +247,7 @@ static int launch_tiles_impl(const void* pred, const void* mask, float mscale, i
     set_error("seg_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return COR_ECUDA;
   }
-  k<<<N * tiles, 256, sizeof(SegSmem), st>>>((const TP*)pred, (const TM*)mask, mscale, H, W, Hm, Wm, ns, fa, fg_, t_save, w_save, part);
+  k<<<N * tiles, kSegThreads, sizeof(SegSmem), st>>>((const TP*)pred, (const TM*)mask, mscale, H, W, Hm, Wm, ns, fa, fg_, t_save, w_save, part);
   return check_launch("seg_loss_tile_kernel");
 }
 

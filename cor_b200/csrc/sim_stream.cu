@@ -10,7 +10,6 @@
 namespace cor {
 
 constexpr int kQT = 16;          // queries per tile (one lane per query after the transposed reduce)
-constexpr int kMaxDL = 8;        // feature elements per lane per vector (16 B of bf16)
 
 // ---- row L2 normalise ------------------------------------------------------------------------------
 template <typename T>
