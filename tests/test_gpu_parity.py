@@ -367,3 +367,57 @@ def test_full_size_properties_config2():
     assert torch.allclose(S[:, :64].t(), St, atol=1e-6)
     idx, sc = region.topk_regions(R, q, 10, engine="stream")
     assert (sc[:, 1:] <= sc[:, :-1]).all() and int(idx.max()) < B * M
+
+
+def test_config1_full_size_fp32_vs_cpu_port():
+    """BASELINE config 1 at full size: 1 triplet, 64 candidate 1024x1024 masks, fp32 everything.
+    The CUDA path (exact fp32 streaming engines) against the ATen port of the reference, loss parts
+    and the gradient of the composed query."""
+    from cor_b200 import region, synth
+    from oracle import aten_port as ap
+    d = synth.make_triplets(101, B=1, M=64, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, degenerate=True)
+    p, e, c = cu(d["pred"], True), cu(d["emb"], True), cu(d["comb"], True)
+    out = region.region_step(p, e, c, cu(d["masks"]), tau=0.07, gather=False, pool_engine="stream", sim_engine="stream")
+    pc, ec, cc = (torch.from_numpy(d[k]).requires_grad_(True) for k in ("pred", "emb", "comb"))
+    ref, regions = ap.region_step_loss(pc, ec, cc, torch.from_numpy(d["masks"]), tau=0.07)
+    close(out.loss, ref.item(), rtol=1e-3, atol=1e-4)
+    close(out.regions.reshape(64, 256), regions.detach().numpy(), rtol=1e-3, atol=1e-4)
+    out.loss.backward()
+    ref.backward()
+    close(c.grad, cc.grad.numpy(), rtol=5e-3, atol=5e-5)
+    close(p.grad, pc.grad.numpy(), rtol=2e-3, atol=1e-8)
+
+
+def test_ragged_and_odd_shapes():
+    """Shapes that hit every scalar / tail path: odd widths, non-multiple-of-16 resample ratios, masks
+    narrower than a vector, P not a multiple of the vector width, C not a multiple of the CTA tile."""
+    from cor_b200 import ops, synth
+    from oracle import np_oracle as no
+    rng = np.random.default_rng(7)
+    for (B, M, C, h, w, H, W) in [(2, 3, 17, 9, 13, 37, 51), (1, 5, 40, 27, 27, 384, 384), (3, 1, 8, 5, 7, 5, 7), (1, 2, 130, 6, 6, 100, 90)]:
+        emb = rng.standard_normal((B, C, h, w)).astype(np.float32)
+        masks = synth.make_masks(rng, B, M, H, W, soft=True, degenerate=False)
+        p = ops.region_pool(cu(emb), cu(masks), transform=ops.W_CLAMP, normalize=True, pair=True, engine="stream")
+        close(p.fg, no.multi_mask_pool(emb, masks), rtol=2e-4, atol=2e-5)
+        close(p.bg, no.multi_mask_pool(emb, masks, background=True), rtol=2e-4, atol=2e-5)
+        st = p.stats.cpu().numpy()
+        np.testing.assert_allclose(st[:, 0], masks.reshape(B * M, -1).astype(np.float64).sum(1), rtol=1e-5)
+    for (N, H, W, Hm, Wm) in [(2, 33, 47, 70, 131), (1, 65, 64, 65, 64), (3, 7, 200, 28, 800)]:
+        pred = rng.standard_normal((N, 1, H, W)).astype(np.float32)
+        mask = synth.make_masks(rng, N, 1, Hm, Wm, soft=True, degenerate=False)
+        close(ops.seg_loss(cu(pred), cu(mask)), no.segmentation_loss(pred, mask), rtol=1e-4, atol=1e-6)
+
+
+def test_val_post_generic_scale_and_u8_gt():
+    from cor_b200 import ops, synth
+    from oracle import np_oracle as no
+    rng = np.random.default_rng(9)
+    pred = synth.make_logits(rng, 2, 24, 40)
+    gt = synth.make_masks(rng, 2, 1, 60, 100, degenerate=False)
+    r = ops.val_postprocess(cu(pred), size=(60, 100), gt=cu((gt * 255).astype(np.uint8)), want_hard=True)
+    ref = no.val_postprocess(pred, (60, 100))
+    close(r["post"], ref, rtol=1e-5, atol=3e-6)
+    assert (r["hard"].cpu().numpy() == no.binarize(ref)).mean() >= 0.999
+    m = no.soft_metrics(ref, gt)
+    for i, k in enumerate(("dice", "mae", "iou", "mdice", "miou")):
+        close(r["metrics"][:, i], m[k], rtol=1e-4, atol=1e-6)
