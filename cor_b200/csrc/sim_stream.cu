@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(1024) infonce_fwd_kernel(const bf16* __restric
 // grid = region CTAs (persistent), block = 256; loops over query tiles of 16 so that every region row
 // is owned by exactly one warp (deterministic, no atomics).  qpart [gridDim.x][Nq][D] per-CTA partials
 // of g_queries are reduced in fixed order by infonce_bwd_q_kernel.
+template <bool WANT_R>
 __global__ void __launch_bounds__(256, 1) infonce_bwd_kernel(const bf16* __restrict__ regions, const bf16* __restrict__ queries,
                                                              const long long* __restrict__ targets, const float* __restrict__ lse,
                                                              int Nr, int Nq, int D, float inv_tau, const float* __restrict__ g_loss,
-                                                             float* __restrict__ g_regions, float* __restrict__ qpart) {
+                                                             float g_mul, float* __restrict__ g_regions, float* __restrict__ qpart) {
   extern __shared__ float smem[];
   float* qs = smem;                    // [kQT][D]
   float* red = smem + kQT * D;         // [8 warps][kQT][D] reduction scratch (reuses after the row loop)
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(256, 1) infonce_bwd_kernel(const bf16* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D / 8;              // <= 32: one 16-byte vector per lane
   const bool has = lane < nvec;
-  const float gscale = g_loss[0] * inv_tau / (float)Nq;
+  const float gscale = g_loss[0] * g_mul * inv_tau / (float)Nq;
   for (int q0 = 0; q0 < Nq; q0 += kQT) {
     __syncthreads();
     for (int i = threadIdx.x; i < kQT * D; i += blockDim.x) {
@@ -219,13 +220,15 @@ __global__ void __launch_bounds__(256, 1) infonce_bwd_kernel(const bf16* __restr
         if (has) {
           const float4 x = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8]);
           const float4 y = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8 + 4]);
-          gr[0] = fmaf(c, x.x, gr[0]); gr[1] = fmaf(c, x.y, gr[1]); gr[2] = fmaf(c, x.z, gr[2]); gr[3] = fmaf(c, x.w, gr[3]);
-          gr[4] = fmaf(c, y.x, gr[4]); gr[5] = fmaf(c, y.y, gr[5]); gr[6] = fmaf(c, y.z, gr[6]); gr[7] = fmaf(c, y.w, gr[7]);
+          if (WANT_R) {
+            gr[0] = fmaf(c, x.x, gr[0]); gr[1] = fmaf(c, x.y, gr[1]); gr[2] = fmaf(c, x.z, gr[2]); gr[3] = fmaf(c, x.w, gr[3]);
+            gr[4] = fmaf(c, y.x, gr[4]); gr[5] = fmaf(c, y.y, gr[5]); gr[6] = fmaf(c, y.z, gr[6]); gr[7] = fmaf(c, y.w, gr[7]);
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) dq[q][e] = fmaf(c, f[e], dq[q][e]);
         }
       }
-      if (has) {
+      if (WANT_R && has) {
         float4* o = reinterpret_cast<float4*>(g_regions + r * D + lane * 8);
         if (q0 == 0) {
           o[0] = make_float4(gr[0], gr[1], gr[2], gr[3]);
@@ -251,6 +254,88 @@ __global__ void __launch_bounds__(256, 1) infonce_bwd_kernel(const bf16* __restr
       float t = 0.f;
       for (int w = 0; w < 8; ++w) t += red[w * kQT * D + i];
       qpart[((long long)blockIdx.x * Nq + q0 + q) * D + (i % D)] = t;
+    }
+  }
+}
+
+// g_regions only (no dQ): all queries (chunks of kRQ) stay in shared memory, every region row is read once
+// and its gradient accumulates in registers across ALL query tiles -- one write per row, no block syncs
+// inside the row loop.  This is the (my regions, all queries) half of the collective-free multi-rank backward.
+constexpr int kRQ = 128;
+__global__ void __launch_bounds__(256, 1) infonce_bwd_regions_kernel(const bf16* __restrict__ regions, const bf16* __restrict__ queries,
+                                                                     const long long* __restrict__ targets, const float* __restrict__ lse,
+                                                                     int Nr, int Nq, int D, float inv_tau, const float* __restrict__ g_loss,
+                                                                     float g_mul, float* __restrict__ g_regions) {
+  extern __shared__ float qs[];        // [kRQ][D]
+  __shared__ float lse_s[kRQ];
+  __shared__ long long tgt_s[kRQ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = D / 8;
+  const bool has = lane < nvec;
+  const float gscale = g_loss[0] * g_mul * inv_tau / (float)Nq;
+  for (int qc0 = 0; qc0 < Nq; qc0 += kRQ) {
+    const int qn = min(kRQ, Nq - qc0);
+    const int qn16 = (qn + kQT - 1) / kQT * kQT;
+    __syncthreads();
+    for (int i = threadIdx.x; i < qn16 * D; i += blockDim.x) {
+      const int q = i / D, d = i % D;
+      qs[i] = q < qn ? __bfloat162float(queries[(long long)(qc0 + q) * D + d]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < qn16; i += blockDim.x) {
+      lse_s[i] = i < qn ? lse[qc0 + i] : 0.f;
+      tgt_s[i] = i < qn ? targets[qc0 + i] : -1;
+    }
+    __syncthreads();
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < Nr; r += (long long)gridDim.x * 8) {
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (has) {
+        const uint4 raw = ld_stream16(reinterpret_cast<const uint4*>(regions + r * D) + lane);
+        f[0] = bf16lo(raw.x); f[1] = bf16hi(raw.x); f[2] = bf16lo(raw.y); f[3] = bf16hi(raw.y);
+        f[4] = bf16lo(raw.z); f[5] = bf16hi(raw.z); f[6] = bf16lo(raw.w); f[7] = bf16hi(raw.w);
+      }
+      float gr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int qt = 0; qt < qn16; qt += kQT) {
+        const float* qb = qs + (size_t)qt * D + lane * 8;
+        float a[kQT];
+#pragma unroll
+        for (int q = 0; q < kQT; ++q) {
+          float t = 0.f;
+          if (has) {
+            const float4 x = *reinterpret_cast<const float4*>(qb + q * D);
+            const float4 y = *reinterpret_cast<const float4*>(qb + q * D + 4);
+            t = f[0] * x.x + f[1] * x.y + f[2] * x.z + f[3] * x.w + f[4] * y.x + f[5] * y.y + f[6] * y.z + f[7] * y.w;
+          }
+          a[q] = t;
+        }
+        const float sv = transpose_reduce16(a, lane);
+        float coef = 0.f;
+        if (lane < kQT && qt + lane < qn) {
+          coef = __expf(sv * inv_tau - lse_s[qt + lane]);
+          if (tgt_s[qt + lane] == r) coef -= 1.f;
+          coef *= gscale;
+        }
+#pragma unroll
+        for (int q = 0; q < kQT; ++q) {
+          const float c = __shfl_sync(0xffffffffu, coef, q);
+          if (has) {
+            const float4 x = *reinterpret_cast<const float4*>(qb + q * D);
+            const float4 y = *reinterpret_cast<const float4*>(qb + q * D + 4);
+            gr[0] = fmaf(c, x.x, gr[0]); gr[1] = fmaf(c, x.y, gr[1]); gr[2] = fmaf(c, x.z, gr[2]); gr[3] = fmaf(c, x.w, gr[3]);
+            gr[4] = fmaf(c, y.x, gr[4]); gr[5] = fmaf(c, y.y, gr[5]); gr[6] = fmaf(c, y.z, gr[6]); gr[7] = fmaf(c, y.w, gr[7]);
+          }
+        }
+      }
+      if (has) {
+        float4* o = reinterpret_cast<float4*>(g_regions + r * D + lane * 8);
+        if (qc0 == 0) {
+          o[0] = make_float4(gr[0], gr[1], gr[2], gr[3]);
+          o[1] = make_float4(gr[4], gr[5], gr[6], gr[7]);
+        } else {
+          float4 p0 = o[0], p1 = o[1];
+          o[0] = make_float4(p0.x + gr[0], p0.y + gr[1], p0.z + gr[2], p0.w + gr[3]);
+          o[1] = make_float4(p1.x + gr[4], p1.y + gr[5], p1.z + gr[6], p1.w + gr[7]);
+        }
+      }
     }
   }
 }
@@ -478,19 +563,33 @@ extern "C" int cor_infonce_fwd(const void* regions, const void* queries, const l
 }
 
 extern "C" int cor_infonce_bwd(const void* regions, const void* queries, const long long* targets, const float* lse, int Nr,
-                               int Nq, int D, float inv_tau, const float* g_loss, float* g_regions, float* g_queries, void* work,
-                               cor_stream_t stream) {
-  COR_REQUIRE(regions && queries && targets && lse && g_loss && g_regions && g_queries && work, "cor_infonce_bwd: null pointer");
+                               int Nq, int D, float inv_tau, const float* g_loss, float g_mul, float* g_regions, float* g_queries,
+                               void* work, cor_stream_t stream) {
+  COR_REQUIRE(regions && queries && targets && lse && g_loss && (g_regions || g_queries), "cor_infonce_bwd: null pointer");
+  COR_REQUIRE(!g_queries || work, "cor_infonce_bwd: g_queries needs a work buffer");
   COR_REQUIRE(D % 8 == 0 && D <= 256, "cor_infonce_bwd: streaming backward supports D %% 8 == 0 and D <= 256 (D=%d)", D);
   COR_REQUIRE((((uintptr_t)regions) & 15) == 0 && (((uintptr_t)g_regions) & 15) == 0, "cor_infonce_bwd: 16-byte alignment required");
-  const size_t smem = (size_t)(kQT * D + 8 * kQT * D) * sizeof(float);
   cudaStream_t st = as_stream(stream);
-  COR_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int ctas = sm_count();
   const int need = ceil_div(Nr, 8);
   if (ctas > need) ctas = need;
-  infonce_bwd_kernel<<<ctas, 256, smem, st>>>((const bf16*)regions, (const bf16*)queries, targets, lse, Nr, Nq, D, inv_tau, g_loss,
-                                             g_regions, (float*)work);
+  if (!g_queries) {
+    const size_t smem_r = (size_t)kRQ * D * sizeof(float);
+    COR_CUDA(cudaFuncSetAttribute(infonce_bwd_regions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    infonce_bwd_regions_kernel<<<ctas, 256, smem_r, st>>>((const bf16*)regions, (const bf16*)queries, targets, lse, Nr, Nq, D, inv_tau,
+                                                         g_loss, g_mul, g_regions);
+    return check_launch("infonce_bwd_regions_kernel");
+  }
+  const size_t smem = (size_t)(kQT * D + 8 * kQT * D) * sizeof(float);
+  if (g_regions) {
+    COR_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infonce_bwd_kernel<true><<<ctas, 256, smem, st>>>((const bf16*)regions, (const bf16*)queries, targets, lse, Nr, Nq, D, inv_tau, g_loss,
+                                                     g_mul, g_regions, (float*)work);
+  } else {
+    COR_CUDA(cudaFuncSetAttribute(infonce_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    infonce_bwd_kernel<false><<<ctas, 256, smem, st>>>((const bf16*)regions, (const bf16*)queries, targets, lse, Nr, Nq, D, inv_tau, g_loss,
+                                                      g_mul, nullptr, (float*)work);
+  }
   int rc = check_launch("infonce_bwd_kernel");
   if (rc) return rc;
   const long long n = (long long)Nq * D;

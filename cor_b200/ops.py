@@ -474,7 +474,7 @@ class _InfoNCEFn(torch.autograd.Function):
         gq = torch.empty((Nq, D), dtype=torch.float32, device=dev)
         work = _work(lib.cor_sim_work_bytes(Nq, Nr, D), dev)
         gl = g.reshape(1).float().contiguous()
-        _call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(tg), ptr(lse), Nr, Nq, D, _f(inv_tau), ptr(gl), ptr(gr), ptr(gq), ptr(work))
+        _call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(tg), ptr(lse), Nr, Nq, D, _f(inv_tau), ptr(gl), _f(1.0), ptr(gr), ptr(gq), ptr(work))
         return (gr.view(rshape).to(rdt) if r_need else None), (gq.view(qshape).to(qdt) if q_need else None), None, None, None, None
 
 

@@ -8,6 +8,7 @@ column of the similarity matrix equals the cosine inside ``fg_feat_similarity_lo
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -131,21 +132,39 @@ class _FusedStepFn(torch.autograd.Function):
         q16 = comb_c.to(torch.bfloat16)
         rank, ws = cdist.world()
         n_local = B * M
+        inv_tau = 1.0 / float(tau)
+        # A/B on one 8xB200 box (profiles/README.md): reduce-scatter of the region gradient 0.951 ms/step, collective-free
+        # variant 0.965 ms/step -> the reduce-scatter stays the default; COR_STEP_BWD=local selects the other.
+        local_bwd = os.environ.get("COR_STEP_BWD", "reduce_scatter") == "local"
         if gather and ws > 1:
             r16 = torch.empty((ws * n_local, Cc), dtype=torch.bfloat16, device=dev)
             torch.distributed.all_gather_into_tensor(r16, fg16)
             offset = rank * n_local
+            if local_bwd:
+                # A second small all-gather (the queries) replaces the backward's reduce-scatter: every rank scores
+                # ALL queries against ALL regions (same HBM-bound cost as scoring its own), which gives it the
+                # log-sum-exp of the remote queries too, so the backward needs no collective at all.
+                q_all = torch.empty((ws * B, Cc), dtype=torch.bfloat16, device=dev)
+                torch.distributed.all_gather_into_tensor(q_all, q16)
+                _, lse_all = ops._sim_forward(r16, q_all, inv_tau, False, True, sim_engine)
+                lse = lse_all[rank * B:(rank + 1) * B]
+                ar = torch.arange(ws * B, device=dev, dtype=torch.int64)
+                tgt_all = (ar // B) * n_local + (ar % B) * M - offset       # target rows local to THIS rank
+            else:
+                q_all = lse_all = tgt_all = None
+                _, lse = ops._sim_forward(r16, q16, inv_tau, False, True, sim_engine)
         else:
             r16, offset, ws = fg16, 0, 1
+            q_all = lse_all = tgt_all = None
+            _, lse = ops._sim_forward(r16, q16, inv_tau, False, True, sim_engine)
         targets = torch.arange(B, device=dev, dtype=torch.int64) * M + offset
-        inv_tau = 1.0 / float(tau)
-        _, lse = ops._sim_forward(r16, q16, inv_tau, False, True, sim_engine)
         nce = torch.empty(1, **f32)
         tgt = torch.empty((B,), **f32)
         call("cor_infonce_fwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), r16.shape[0], B, Cc, _f(inv_tau), ptr(nce), ptr(tgt))
         loss = torch.empty(1, **f32)
         call("cor_step_combine", dev, ptr(out8), ptr(out4), ptr(nce), _f(w_fg), _f(w_bg), _f(nce_weight), ptr(loss))
-        ctx.save_for_backward(pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32)
+        ctx.save_for_backward(pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32,
+                              fg16, q_all, lse_all, tgt_all)
         ctx.cfg = (B, M, Cc, h, w, float(inv_tau), float(nce_weight), int(bg_mode), float(w_fg), float(w_bg), ws, offset, n_local,
                    pred.dtype, emb.dtype, comb.dtype, tuple(comb.shape), need_pred, need_emb, comb.requires_grad)
         ctx.mark_non_differentiable(fg, out8, out4, nce)
@@ -155,7 +174,8 @@ class _FusedStepFn(torch.autograd.Function):
     def backward(ctx, g_loss, *_unused):
         from . import _lib as L
         ptr, _f, _ll, call = ops.ptr, ops._f, ops._ll, ops._call
-        (pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32) = ctx.saved_tensors
+        (pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32,
+         fg16, q_all, lse_all, tgt_all) = ctx.saved_tensors
         (B, M, Cc, h, w, inv_tau, nce_weight, bg_mode, w_fg, w_bg, ws, offset, n_local, pred_dt, emb_dt, comb_dt, comb_shape,
          need_pred, need_emb, need_comb) = ctx.cfg
         dev = fg.device
@@ -170,18 +190,27 @@ class _FusedStepFn(torch.autograd.Function):
             call("cor_seg_loss_bwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _f(1.0), _f(1.0),
                  ptr(g), ptr(g_pred), L.dtype_code(g_pred))
             g_pred = g_pred.to(pred_dt)
-        # InfoNCE backward first: it WRITES g_regions (all gathered rows) and g_queries ...
+        # InfoNCE backward first: it WRITES g_regions (this rank's rows) and g_queries ...
         Nr = r16.shape[0]
-        g_regions = torch.empty((Nr, Cc), **f32)
+        g_regions = torch.empty((n_local, Cc), **f32)
         g_q = torch.empty((B, Cc), **f32)
         work = ops._work(lib.cor_sim_work_bytes(B, Nr, Cc), dev)
         g_nce = g * nce_weight
-        call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), ptr(g_regions),
-             ptr(g_q), ptr(work))
-        if ws > 1:
-            local = torch.empty((n_local, Cc), **f32)
-            torch.distributed.reduce_scatter_tensor(local, g_regions, op=torch.distributed.ReduceOp.SUM)
-            g_regions = local
+        if ws > 1 and q_all is not None:
+            # (all regions, my queries) -> g_queries ; (my regions, ALL queries) -> g_regions.  Every rank's loss is the
+            # mean over its own B queries, so the sum over ranks of d loss_j / d my_regions carries the factor ws.
+            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), _f(1.0), None,
+                 ptr(g_q), ptr(work))
+            call("cor_infonce_bwd", dev, ptr(fg16), ptr(q_all), ptr(tgt_all), ptr(lse_all), n_local, ws * B, Cc, _f(inv_tau), ptr(g_nce),
+                 _f(float(ws)), ptr(g_regions), None, None)
+        elif ws > 1:
+            g_all = torch.empty((Nr, Cc), **f32)
+            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), _f(1.0),
+                 ptr(g_all), ptr(g_q), ptr(work))
+            torch.distributed.reduce_scatter_tensor(g_regions, g_all, op=torch.distributed.ReduceOp.SUM)
+        else:
+            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), _f(1.0),
+                 ptr(g_regions), ptr(g_q), ptr(work))
         # ... then the fg/bg backward ADDS its GT-row gradients into g_regions (row b*M) and g_queries
         g2 = torch.cat([g * w_fg, g * w_bg])
         g_bg = torch.empty((B, Cc), **f32) if bg_mode == 1 else None

@@ -175,9 +175,11 @@ int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr, int Nq, i
 /* loss = mean_q (lse[q] - S[q, target[q]] / tau); tgt_logit [Nq] is S[q,target[q]] (f32). */
 int cor_infonce_fwd(const void* regions, const void* queries, const long long* targets, const float* lse,
                     int Nr, int Nq, int D, float inv_tau, float* loss, float* tgt_logit, cor_stream_t stream);
-/* g_regions [Nr, D] f32, g_queries [Nq, D] f32 for upstream scalar *g_loss. */
+/* g_regions [Nr, D] f32 and/or g_queries [Nq, D] f32 (either may be NULL) for upstream scalar *g_loss * g_mul.
+ * A rank of a data-parallel job calls it twice -- (all regions, its queries) -> g_queries and
+ * (its regions, all queries; g_mul = world size) -> g_regions -- so the backward needs no collective. */
 int cor_infonce_bwd(const void* regions, const void* queries, const long long* targets, const float* lse,
-                    int Nr, int Nq, int D, float inv_tau, const float* g_loss, float* g_regions,
+                    int Nr, int Nq, int D, float inv_tau, const float* g_loss, float g_mul, float* g_regions,
                     float* g_queries, void* work, cor_stream_t stream);
 
 /* Top-k retrieval: per query the k best regions under (score desc, index asc), where score is the

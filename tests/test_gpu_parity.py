@@ -421,3 +421,39 @@ def test_val_post_generic_scale_and_u8_gt():
     m = no.soft_metrics(ref, gt)
     for i, k in enumerate(("dice", "mae", "iou", "mdice", "miou")):
         close(r["metrics"][:, i], m[k], rtol=1e-4, atol=1e-6)
+
+
+def test_collective_free_infonce_backward_emulating_two_ranks():
+    """The multi-rank step computes d(sum_j loss_j)/d(my regions) locally from (my regions, ALL queries) and
+    d loss_me / d(my queries) from (ALL regions, my queries): emulate world_size 2 on one GPU and compare with
+    autograd over the concatenated problem."""
+    from cor_b200 import _lib as L
+    from cor_b200 import ops, synth
+    ws, B, M, D = 2, 5, 12, 128
+    n_local = B * M
+    g = synth.make_gallery(131, ws * n_local, ws * B, D=D)
+    R = cu(g["regions"], True)
+    Q = cu(g["queries"], True)
+    tau = 0.07
+    tg = [torch.arange(B, device=dev()) * M + j * n_local for j in range(ws)]
+    total = sum(ops.infonce_loss(R, Q[j * B:(j + 1) * B], tg[j], tau, engine="stream") for j in range(ws))
+    total.backward()
+    r16 = R.detach().to(torch.bfloat16).contiguous()
+    q16 = Q.detach().to(torch.bfloat16).contiguous()
+    _, lse_all = ops._sim_forward(r16, q16, 1 / tau, False, True, "stream")
+    one = torch.ones(1, device=dev())
+    lib = L.load()
+    for rank in range(ws):
+        g_regions = torch.empty(n_local, D, device=dev())
+        g_q = torch.empty(B, D, device=dev())
+        work = ops._work(lib.cor_sim_work_bytes(ws * B, ws * n_local, D), dev())
+        offset = rank * n_local
+        tgt_all = torch.cat(tg) - offset
+        my_q = q16[rank * B:(rank + 1) * B].contiguous()
+        my_r = r16[offset:offset + n_local].contiguous()
+        ops._call("cor_infonce_bwd", dev(), ops.ptr(r16), ops.ptr(my_q), ops.ptr(tg[rank].contiguous()), ops.ptr(lse_all[rank * B:(rank + 1) * B].contiguous()),
+                  ws * n_local, B, D, ops._f(1 / tau), ops.ptr(one), ops._f(1.0), None, ops.ptr(g_q), ops.ptr(work))
+        ops._call("cor_infonce_bwd", dev(), ops.ptr(my_r), ops.ptr(q16), ops.ptr(tgt_all.contiguous()), ops.ptr(lse_all), n_local, ws * B, D,
+                  ops._f(1 / tau), ops.ptr(one), ops._f(float(ws)), ops.ptr(g_regions), None, None)
+        close(g_q, Q.grad[rank * B:(rank + 1) * B].cpu().numpy(), rtol=1e-4, atol=1e-6)
+        close(g_regions, R.grad[offset:offset + n_local].cpu().numpy(), rtol=1e-4, atol=1e-6)
