@@ -28,6 +28,21 @@ __device__ __forceinline__ float upsampled_sigmoid(const TP* __restrict__ p, int
   return sigmoid_acc(z);
 }
 
+// vailder.py:427-430,466: sigmoid + min-max at the LOGIT resolution first, then bilinear resize of the
+// normalised map (cv2.resize INTER_LINEAR == align_corners=False sampling).  Since the tap weights sum to 1,
+// resize((s - mn) / den) == (resize(s) - mn) / den: interpolate the sigmoids, normalise afterwards.
+template <typename TP>
+__device__ __forceinline__ float resized_sigmoid(const TP* __restrict__ p, int H, int W, float sh, float sw, int oy, int ox) {
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  src_index(sh, oy, H, y0, y1, ly0, ly1);
+  src_index(sw, ox, W, x0, x1, lx0, lx1);
+  const TP* r0 = p + (long long)y0 * W;
+  const TP* r1 = p + (long long)y1 * W;
+  return ly0 * (lx0 * sigmoid_acc(to_f<TP>(__ldg(r0 + x0))) + lx1 * sigmoid_acc(to_f<TP>(__ldg(r0 + x1)))) +
+         ly1 * (lx0 * sigmoid_acc(to_f<TP>(__ldg(r1 + x0))) + lx1 * sigmoid_acc(to_f<TP>(__ldg(r1 + x1))));
+}
+
 // All threads of the block reduce the per-chunk (min,max) partials of one sample (a serial loop in one
 // thread would put ~chunks L2 round trips in front of every CTA).
 __device__ __forceinline__ void block_minmax(const float* __restrict__ part, int chunks, float& s_mn, float& s_mx) {
@@ -78,7 +93,7 @@ __global__ void __launch_bounds__(256) val_minmax_kernel(const TP* __restrict__ 
 
 // metric partial sums per CTA: {sum p*g, sum p, sum g, sum |p-g|}
 template <typename TP, typename TG>
-__global__ void __launch_bounds__(256) val_write_kernel(const TP* __restrict__ pred, int H, int W, int Ho, int Wo,
+__global__ void __launch_bounds__(256) val_write_kernel(const TP* __restrict__ pred, int H, int W, int Ho, int Wo, int post_first,
                                                         const float* __restrict__ mm_part, int chunks, float* __restrict__ post,
                                                         uint8_t* __restrict__ hard, const TG* __restrict__ gt, float gscale,
                                                         double* __restrict__ met_part) {
@@ -94,7 +109,9 @@ __global__ void __launch_bounds__(256) val_write_kernel(const TP* __restrict__ p
   double acc[4] = {0, 0, 0, 0};
   float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
   for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
-    const float v = (upsampled_sigmoid<TP>(p, H, W, sh, sw, (int)(o / Wo), (int)(o % Wo), same) - mn) / den;
+    const int oy = (int)(o / Wo), ox = (int)(o % Wo);
+    const float sg = (post_first && !same) ? resized_sigmoid<TP>(p, H, W, sh, sw, oy, ox) : upsampled_sigmoid<TP>(p, H, W, sh, sw, oy, ox, same);
+    const float v = (sg - mn) / den;
     const long long g_o = (long long)n * total + o;
     if (post) post[g_o] = v;
     if (hard) hard[g_o] = v > 0.5f ? 255 : 0;
@@ -250,7 +267,7 @@ extern "C" size_t cor_val_post_work_bytes(int N, int Ho, int Wo) {
   return (size_t)N * 1024 * (2 * sizeof(float) + 4 * sizeof(double)) + 64;
 }
 
-extern "C" int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, int Wo, float* post, uint8_t* hard,
+extern "C" int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, int Wo, int post_first, float* post, uint8_t* hard,
                             const void* gt, int gt_dtype, float gt_scale, float* metrics, void* work, cor_stream_t stream) {
   COR_REQUIRE(pred && work && (post || hard || (gt && metrics)), "cor_val_post: nothing to do / null pointer");
   COR_REQUIRE(N > 0 && N <= 65535 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "cor_val_post: bad shape");
@@ -261,7 +278,7 @@ extern "C" int cor_val_post(const void* pred, int pred_dtype, int N, int H, int 
   double* met_part = reinterpret_cast<double*>(work);
   float* mm_part = reinterpret_cast<float*>(met_part + (size_t)N * 1024 * 4);
   dim3 grid(chunks, N);
-  const bool up4 = Ho == 4 * H && Wo == 4 * W && (!post || (((uintptr_t)post) & 15) == 0) && (!hard || (((uintptr_t)hard) & 3) == 0);
+  const bool up4 = !post_first && Ho == 4 * H && Wo == 4 * W && (!post || (((uintptr_t)post) & 15) == 0) && (!hard || (((uintptr_t)hard) & 3) == 0);
   if (up4) {
     int c4 = ceil_div((long long)H * W, 256);
     if (c4 > 1024) c4 = 1024;
@@ -283,12 +300,14 @@ extern "C" int cor_val_post(const void* pred, int pred_dtype, int N, int H, int 
     val_metrics_kernel<<<ceil_div(N, 128), 128, 0, st>>>(met_part, N, c4, (double)total, metrics);
     return check_launch("val_metrics_kernel");
   }
-  if (pred_dtype == COR_F32) val_minmax_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, H, W, Ho, Wo, mm_part);
-  else if (pred_dtype == COR_BF16) val_minmax_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)pred, H, W, Ho, Wo, mm_part);
+  // post_first: the min / max are those of the sigmoid at the logit resolution
+  const int Hmm = post_first ? H : Ho, Wmm = post_first ? W : Wo;
+  if (pred_dtype == COR_F32) val_minmax_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, H, W, Hmm, Wmm, mm_part);
+  else if (pred_dtype == COR_BF16) val_minmax_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)pred, H, W, Hmm, Wmm, mm_part);
   else COR_REQUIRE(false, "cor_val_post: unsupported pred dtype %d", pred_dtype);
   int rc = check_launch("val_minmax_kernel");
   if (rc) return rc;
-#define COR_VW(TP, TG) val_write_kernel<TP, TG><<<grid, 256, 0, st>>>((const TP*)pred, H, W, Ho, Wo, mm_part, chunks, post, hard, (const TG*)gt, gt_scale, met_part)
+#define COR_VW(TP, TG) val_write_kernel<TP, TG><<<grid, 256, 0, st>>>((const TP*)pred, H, W, Ho, Wo, post_first, mm_part, chunks, post, hard, (const TG*)gt, gt_scale, met_part)
   if (pred_dtype == COR_F32 && (!gt || gt_dtype == COR_F32)) COR_VW(float, float);
   else if (pred_dtype == COR_BF16 && (!gt || gt_dtype == COR_F32)) COR_VW(bf16, float);
   else if (pred_dtype == COR_F32 && gt_dtype == COR_U8) COR_VW(float, uint8_t);

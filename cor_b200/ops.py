@@ -503,9 +503,12 @@ def topk_retrieve(regions: torch.Tensor, queries: torch.Tensor, k: int, engine: 
 # validation post-process
 # --------------------------------------------------------------------------------------------------
 def val_postprocess(pred: torch.Tensor, size=None, gt: Optional[torch.Tensor] = None, want_post: bool = True,
-                    want_hard: bool = False, gt_scale: Optional[float] = None):
+                    want_hard: bool = False, gt_scale: Optional[float] = None, post_first: bool = False):
     """sigmoid + per-sample min-max of (optionally upsampled) logits; returns dict with ``post``
-    [N,1,Ho,Wo] f32, ``hard`` uint8 (0/255), ``metrics`` [N,5] {dice,mae,iou,mdice,miou} if gt given."""
+    [N,1,Ho,Wo] f32, ``hard`` uint8 (0/255), ``metrics`` [N,5] {dice,mae,iou,mdice,miou} if gt given.
+    ``post_first=False`` is the in-training validation order (resize logits, then sigmoid + min-max,
+    trainer_v3_g.py:226-231); ``post_first=True`` is the offline evaluator's (sigmoid + min-max at the logit
+    size, then bilinear resize of the map to the ground-truth size and > 0.5, vailder.py:427-430,466,473)."""
     dev = require_cuda(pred, gt)
     pc = _as_supported_float(pred)
     if pc.dim() != 4 or pc.shape[1] != 1:
@@ -524,6 +527,6 @@ def val_postprocess(pred: torch.Tensor, size=None, gt: Optional[torch.Tensor] = 
             raise CorError("val_postprocess: gt must have the output resolution")
         metrics = torch.empty((N, 5), dtype=torch.float32, device=dev)
     work = _work(lib.cor_val_post_work_bytes(N, Ho, Wo), dev)
-    _call("cor_val_post", dev, ptr(pc), dtype_code(pc), N, H, W, Ho, Wo, ptr(post), ptr(hard), ptr(gc),
+    _call("cor_val_post", dev, ptr(pc), dtype_code(pc), N, H, W, Ho, Wo, int(post_first), ptr(post), ptr(hard), ptr(gc),
           (dtype_code(gc) if gc is not None else F32), _f(_mask_scale(gc, gt_scale) if gc is not None else 1.0), ptr(metrics), ptr(work))
     return {"post": post, "hard": hard, "metrics": metrics}

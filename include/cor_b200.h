@@ -201,7 +201,10 @@ int cor_l2_normalize(const void* x, int x_dtype, int n, int D, float* y_f32, voi
  *   post [N,Ho,Wo] f32 or NULL; hard [N,Ho,Wo] u8 or NULL; metrics [N,5] {dice,mae,iou,mdice,miou}.
  * ---------------------------------------------------------------------------------------- */
 size_t cor_val_post_work_bytes(int N, int Ho, int Wo);
-int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, int Wo, float* post,
+int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, int Wo,
+                 int post_first /* 0: resize logits, then sigmoid + min-max (trainer_v3_g.py:226-231);
+                                   1: sigmoid + min-max at the logit size, then resize the map (vailder.py:427-430,466) */,
+                 float* post,
                  uint8_t* hard, const void* gt, int gt_dtype, float gt_scale, float* metrics, void* work,
                  cor_stream_t stream);
 

@@ -176,6 +176,12 @@ def main():
     if trainer is not None:
         for k in ("dice", "mae", "iou", "mdice", "miou"):
             extra[k] = getattr(trainer, "compute_" + k)(post, t(gt)).numpy()
+    # offline evaluator (vailder.py:427-430,459-473): normalise at 32x32, cv2.resize to the GT size, binarise
+    import cv2
+    gt_hw = (75, 100)
+    resized = np.stack([cv2.resize(post0.numpy()[i, 0], (gt_hw[1], gt_hw[0]), interpolation=cv2.INTER_LINEAR) for i in range(2)])[:, None]
+    save("vailder_hard", pred=pred, resized=resized.astype(np.float32), hard=((resized > 0.5).astype(np.uint8) * 255),
+         gt_hw=np.asarray(gt_hw))
     save("val_post", pred=pred, post_up=post.numpy(), post_same=post0.numpy(), gt=gt,
          hard_up=((post.numpy() > 0.5).astype(np.uint8) * 255), **extra)
 

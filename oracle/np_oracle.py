@@ -273,6 +273,13 @@ def val_postprocess(pred, out_hw=None) -> np.ndarray:
     return ((p - mn) / (mx - mn + F32(1e-8))).astype(F32)
 
 
+def vailder_postprocess(pred, gt_hw) -> np.ndarray:
+    """Offline evaluator order, utils/vailder.py:427-430 then :466: sigmoid + per-sample min-max at the logit
+    size, then ``cv2.resize(..., INTER_LINEAR)`` of each normalised map to the ground-truth size.  For float32
+    input cv2's INTER_LINEAR samples with the same half-pixel rule and edge clamps as align_corners=False."""
+    return bilinear_resize(val_postprocess(pred), gt_hw)
+
+
 def binarize(p: np.ndarray) -> np.ndarray:
     """utils/vailder.py:473: (p > 0.5) * 255 as uint8."""
     return ((np.asarray(p) > 0.5).astype(np.uint8) * 255).astype(np.uint8)

@@ -457,3 +457,13 @@ def test_collective_free_infonce_backward_emulating_two_ranks():
                   ops._f(1 / tau), ops.ptr(one), ops._f(float(ws)), ops.ptr(g_regions), None, None)
         close(g_q, Q.grad[rank * B:(rank + 1) * B].cpu().numpy(), rtol=1e-4, atol=1e-6)
         close(g_regions, R.grad[offset:offset + n_local].cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_vailder_offline_order_golden():
+    """Offline evaluator order (vailder.py:427-430,466,473) on the device vs the cv2-generated golden."""
+    from cor_b200 import ops
+    g = load_golden("vailder_hard")
+    hw = tuple(int(v) for v in g["gt_hw"])
+    r = ops.val_postprocess(cu(g["pred"]), size=hw, want_hard=True, post_first=True)
+    close(r["post"], g["resized"], rtol=1e-5, atol=3e-6)
+    assert (r["hard"].cpu().numpy() == g["hard"]).mean() >= 0.999

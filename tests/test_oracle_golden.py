@@ -128,3 +128,12 @@ def test_val_post():
     for k in ("dice", "mae", "iou", "mdice", "miou"):
         if k in g:
             close(m[k], g[k], rtol=1e-5)
+
+
+def test_vailder_offline_binarisation():
+    """utils/vailder.py:427-430,466,473 (sigmoid + min-max at the logit size, cv2.resize to the GT size, > 0.5)
+    generated with the real cv2; the oracle's bilinear restatement must agree on >= 99.9 % of the pixels."""
+    g = load_golden("vailder_hard")
+    out = no.vailder_postprocess(g["pred"], tuple(int(v) for v in g["gt_hw"]))
+    close(out, g["resized"], rtol=1e-5, atol=2e-6)
+    assert (no.binarize(out) == g["hard"]).mean() >= 0.999
