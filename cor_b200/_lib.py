@@ -68,7 +68,7 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_pool_bwd_maps", i, p, i, p, ll, p, p, p, i, i, i, i, p, p)
         _sig(lib, "cor_fgbg_aux_floats", sz, i, i)
         _sig(lib, "cor_fgbg_loss_fwd", i, p, ll, p, ll, p, ll, p, ll, i, i, i, p, p, p)
-        _sig(lib, "cor_fgbg_loss_bwd", i, p, ll, p, ll, p, ll, i, i, i, p, p, p, p, ll, i, p, ll, p, ll, i, p)
+        _sig(lib, "cor_fgbg_loss_bwd", i, p, ll, p, ll, p, ll, i, i, i, p, p, p, ll, f, f, p, ll, i, p, ll, p, ll, i, p)
         _sig(lib, "cor_step_combine", i, p, p, p, f, f, f, p, p)
         _sig(lib, "cor_seg_loss_work_bytes", sz, i, i, i)
         _sig(lib, "cor_seg_loss_fwd", i, p, i, p, i, f, i, i, i, i, i, ll, f, f, f, f, f, p, p, p, p, p, p)

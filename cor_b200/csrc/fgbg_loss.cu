@@ -90,16 +90,17 @@ __global__ void __launch_bounds__(1024) fgbg_reduce_kernel(const float* __restri
 __global__ void __launch_bounds__(128) fgbg_bwd_kernel(const float* __restrict__ fg, long long row_stride, const float* __restrict__ bg,
                                                        long long bg_stride, const float* __restrict__ comb, long long comb_stride, int C,
                                                        int bg_mode, const float* __restrict__ rowstat, const float* __restrict__ colstat,
-                                                       const float* __restrict__ out4, const float* __restrict__ g2,
-                                                       float* __restrict__ g_fg, long long gfg_stride, int fg_acc,
+                                                       const float* __restrict__ out4, const float* __restrict__ g2, long long g2_stride,
+                                                       float gw_fg, float gw_bg, float* __restrict__ g_fg, long long gfg_stride, int fg_acc,
                                                        float* __restrict__ g_bg, long long gbg_stride, float* __restrict__ g_comb,
                                                        long long gcomb_stride, int comb_acc) {
   const int i = blockIdx.x;
   const float* r = rowstat + (long long)i * 8;
   const float nfg = out4[2], nbg = out4[3];
-  const float sf = (r[5] > 0.f && nfg > 0.f) ? -g2[0] / nfg : 0.f;            // d loss_fg / d cos_fg_i
-  const float sb = (bg && bg_mode == 1 && r[6] > 0.f && nbg > 0.f) ? g2[1] / nbg : 0.f;
-  const float quirk = (bg && bg_mode == 0 && r[6] > 0.f && nbg > 0.f) ? g2[1] / (nbg * (float)C) : 0.f;
+  const float gf_up = g2[0] * gw_fg, gb_up = g2[g2_stride] * gw_bg;            // upstream scalars (x caller weights)
+  const float sf = (r[5] > 0.f && nfg > 0.f) ? -gf_up / nfg : 0.f;            // d loss_fg / d cos_fg_i
+  const float sb = (bg && bg_mode == 1 && r[6] > 0.f && nbg > 0.f) ? gb_up / nbg : 0.f;
+  const float quirk = (bg && bg_mode == 0 && r[6] > 0.f && nbg > 0.f) ? gb_up / (nbg * (float)C) : 0.f;
   const float cf = r[0], cb = r[1], nf = r[2], nb = r[3], nq = r[4];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float a = fg[i * row_stride + c], x = comb[i * comb_stride + c];
@@ -150,11 +151,11 @@ extern "C" int cor_fgbg_loss_fwd(const float* fg_rows, long long fg_stride, cons
 
 extern "C" int cor_fgbg_loss_bwd(const float* fg_rows, long long fg_stride, const float* bg_rows, long long bg_stride, const float* comb,
                                  long long comb_stride, int n, int C, int bg_mode, const float* out4, const float* aux, const float* g2,
-                                 float* g_fg_rows, long long gfg_stride, int fg_accumulate, float* g_bg_rows, long long gbg_stride,
+                                 long long g2_stride, float gw_fg, float gw_bg, float* g_fg_rows, long long gfg_stride, int fg_accumulate, float* g_bg_rows, long long gbg_stride,
                                  float* g_comb, long long gcomb_stride, int comb_accumulate, cor_stream_t stream) {
   COR_REQUIRE(fg_rows && comb && out4 && aux && g2 && g_fg_rows && g_comb, "cor_fgbg_loss_bwd: null pointer");
   fgbg_bwd_kernel<<<n, 128, 0, as_stream(stream)>>>(fg_rows, fg_stride, bg_rows, bg_stride, comb, comb_stride, C, bg_mode, aux,
-                                                    aux + (size_t)n * 8, out4, g2, g_fg_rows, gfg_stride, fg_accumulate, g_bg_rows,
+                                                    aux + (size_t)n * 8, out4, g2, g2_stride, gw_fg, gw_bg, g_fg_rows, gfg_stride, fg_accumulate, g_bg_rows,
                                                     gbg_stride, g_comb, gcomb_stride, comb_accumulate);
   return check_launch("fgbg_bwd_kernel");
 }

@@ -196,6 +196,7 @@ class _RegionPoolFn(torch.autograd.Function):
         ctx.save_for_backward(w32 if need_w32 else None, stats, fg, bg, inv_fg, inv_bg, saved_feat,
                               fg_sum if masks.requires_grad else None)
         ctx.mark_non_differentiable(stats)
+        ctx.set_materialize_grads(False)
         outs = (fg.view(B, R // group, Cc), bg.view(B, R // group, Cc) if pair else None, stats, fg16)
         if fg16 is not None:
             ctx.mark_non_differentiable(fg16)
@@ -209,7 +210,7 @@ class _RegionPoolFn(torch.autograd.Function):
         dev = fg.device
         P = h * w
         g_feat = g_maps = None
-        if not (ctx.feat_needs or ctx.maps_need):
+        if not (ctx.feat_needs or ctx.maps_need) or (g_fg is None and g_bg is None):
             return (None,) * 10
         if w32 is None:
             raise CorError("region_pool backward: fp32 weights were not saved")
@@ -305,7 +306,7 @@ class _FgBgFn(torch.autograd.Function):
         g_bg = torch.empty((n, Cc), dtype=torch.float32, device=dev) if bg_c is not None else None
         g_comb = torch.empty((n, Cc), dtype=torch.float32, device=dev)
         _call("cor_fgbg_loss_bwd", dev, ptr(fg_c), _ll(fg_c.stride(0)), ptr(bg_c), _ll(bg_c.stride(0) if bg_c is not None else 0),
-              ptr(comb_c), _ll(comb_c.stride(0)), n, Cc, ctx.bg_mode, ptr(out4), ptr(aux), ptr(g2), ptr(g_fg), _ll(Cc), 0, ptr(g_bg),
+              ptr(comb_c), _ll(comb_c.stride(0)), n, Cc, ctx.bg_mode, ptr(out4), ptr(aux), ptr(g2), _ll(1), _f(1.0), _f(1.0), ptr(g_fg), _ll(Cc), 0, ptr(g_bg),
               _ll(Cc), ptr(g_comb), _ll(Cc), 0)
         return g_fg, g_bg, g_comb.view(ctx.comb_shape).to(ctx.comb_dtype), None, None
 

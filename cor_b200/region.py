@@ -68,6 +68,21 @@ class RegionStepOut:
     regions: torch.Tensor          # [B, M, C] unit rows (detached view for retrieval)
 
 
+_target_cache = {}
+
+
+def _target_rows(dev, B, M, offset):
+    """Row index of every triplet's ground-truth region (b * M + offset), cached per shape."""
+    key = (dev.index, B, M, offset)
+    t = _target_cache.get(key)
+    if t is None:
+        if len(_target_cache) > 64:
+            _target_cache.clear()
+        t = torch.arange(B, device=dev, dtype=torch.int64) * M + offset
+        _target_cache[key] = t
+    return t
+
+
 class _FusedStepFn(torch.autograd.Function):
     """The whole region path as ONE autograd node: every kernel of the forward is launched back to
     back on the current stream, the backward is written out by hand, and no tensor glue (slices,
@@ -157,7 +172,7 @@ class _FusedStepFn(torch.autograd.Function):
             r16, offset, ws = fg16, 0, 1
             q_all = lse_all = tgt_all = None
             _, lse = ops._sim_forward(r16, q16, inv_tau, False, True, sim_engine)
-        targets = torch.arange(B, device=dev, dtype=torch.int64) * M + offset
+        targets = _target_rows(dev, B, M, offset)
         nce = torch.empty(1, **f32)
         tgt = torch.empty((B,), **f32)
         call("cor_infonce_fwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), r16.shape[0], B, Cc, _f(inv_tau), ptr(nce), ptr(tgt))
@@ -168,6 +183,7 @@ class _FusedStepFn(torch.autograd.Function):
         ctx.cfg = (B, M, Cc, h, w, float(inv_tau), float(nce_weight), int(bg_mode), float(w_fg), float(w_bg), ws, offset, n_local,
                    pred.dtype, emb.dtype, comb.dtype, tuple(comb.shape), need_pred, need_emb, comb.requires_grad)
         ctx.mark_non_differentiable(fg, out8, out4, nce)
+        ctx.set_materialize_grads(False)     # no zero-filled gradients for the auxiliary outputs
         return loss[0], out8, out4, nce, fg
 
     @staticmethod
@@ -182,6 +198,8 @@ class _FusedStepFn(torch.autograd.Function):
         lib = L.load()
         P = h * w
         f32 = dict(dtype=torch.float32, device=dev)
+        if g_loss is None:
+            return (None,) * 11
         g = g_loss.reshape(1).float().contiguous()
         g_pred = g_emb = g_comb = None
         if need_pred:
@@ -195,27 +213,25 @@ class _FusedStepFn(torch.autograd.Function):
         g_regions = torch.empty((n_local, Cc), **f32)
         g_q = torch.empty((B, Cc), **f32)
         work = ops._work(lib.cor_sim_work_bytes(B, Nr, Cc), dev)
-        g_nce = g * nce_weight
         if ws > 1 and q_all is not None:
             # (all regions, my queries) -> g_queries ; (my regions, ALL queries) -> g_regions.  Every rank's loss is the
             # mean over its own B queries, so the sum over ranks of d loss_j / d my_regions carries the factor ws.
-            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), _f(1.0), None,
+            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g), _f(nce_weight), None,
                  ptr(g_q), ptr(work))
-            call("cor_infonce_bwd", dev, ptr(fg16), ptr(q_all), ptr(tgt_all), ptr(lse_all), n_local, ws * B, Cc, _f(inv_tau), ptr(g_nce),
-                 _f(float(ws)), ptr(g_regions), None, None)
+            call("cor_infonce_bwd", dev, ptr(fg16), ptr(q_all), ptr(tgt_all), ptr(lse_all), n_local, ws * B, Cc, _f(inv_tau), ptr(g),
+                 _f(float(ws) * nce_weight), ptr(g_regions), None, None)
         elif ws > 1:
             g_all = torch.empty((Nr, Cc), **f32)
-            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), _f(1.0),
+            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g), _f(nce_weight),
                  ptr(g_all), ptr(g_q), ptr(work))
             torch.distributed.reduce_scatter_tensor(g_regions, g_all, op=torch.distributed.ReduceOp.SUM)
         else:
-            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g_nce), _f(1.0),
+            call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g), _f(nce_weight),
                  ptr(g_regions), ptr(g_q), ptr(work))
         # ... then the fg/bg backward ADDS its GT-row gradients into g_regions (row b*M) and g_queries
-        g2 = torch.cat([g * w_fg, g * w_bg])
         g_bg = torch.empty((B, Cc), **f32) if bg_mode == 1 else None
         call("cor_fgbg_loss_bwd", dev, ptr(fg), _ll(M * Cc), ptr(bg), _ll(Cc), ptr(comb_c), _ll(Cc), B, Cc, bg_mode, ptr(out4), ptr(aux),
-             ptr(g2), ptr(g_regions), _ll(M * Cc), 1, ptr(g_bg), _ll(Cc), ptr(g_q), _ll(Cc), 1)
+             ptr(g), _ll(0), _f(w_fg), _f(w_bg), ptr(g_regions), _ll(M * Cc), 1, ptr(g_bg), _ll(Cc), ptr(g_q), _ll(Cc), 1)
         if need_comb:
             g_comb = g_q.view(comb_shape).to(comb_dt)
         if need_emb:

@@ -133,11 +133,13 @@ size_t cor_fgbg_aux_floats(int n, int C);   /* floats of `aux` scratch kept from
 int cor_fgbg_loss_fwd(const float* fg_rows, long long fg_stride, const float* bg_rows, long long bg_stride,
                       const float* comb, long long comb_stride, const float* stats, long long stats_stride,
                       int n, int C, int bg_mode, float* out4, float* aux, cor_stream_t stream);
-/* g_fg_rows / g_comb are written (or, with *_accumulate, added to) at the given row strides, so a caller
- * can fold these gradients straight into larger gradient buffers. */
+/* Upstream gradients: d/d fg-loss = g2[0] * gw_fg, d/d bg-loss = g2[g2_stride] * gw_bg (g2_stride 0 lets one
+ * device scalar feed both).  g_fg_rows / g_comb are written (or, with *_accumulate, added to) at the given
+ * row strides, so a caller can fold these gradients straight into larger gradient buffers. */
 int cor_fgbg_loss_bwd(const float* fg_rows, long long fg_stride, const float* bg_rows, long long bg_stride,
                       const float* comb, long long comb_stride, int n, int C, int bg_mode, const float* out4,
-                      const float* aux, const float* g2, float* g_fg_rows, long long gfg_stride, int fg_accumulate,
+                      const float* aux, const float* g2, long long g2_stride, float gw_fg, float gw_bg,
+                      float* g_fg_rows, long long gfg_stride, int fg_accumulate,
                       float* g_bg_rows, long long gbg_stride, float* g_comb, long long gcomb_stride,
                       int comb_accumulate, cor_stream_t stream);
 /* loss = seg[0] + w_fg * fgbg[0] + w_bg * fgbg[1] + w_nce * nce[0]   (utils/trainer_v3_g.py:67-73; nce may be NULL) */
