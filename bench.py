@@ -206,6 +206,7 @@ def main():
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     ap_.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap_.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
+    ap_.add_argument("--no-u8-variant", action="store_true", help="skip the extra uint8-mask leg reported under 'variants'")
     ap_.add_argument("--pool-engine", default="auto")
     ap_.add_argument("--sim-engine", default="auto")
     args = ap_.parse_args()
@@ -352,6 +353,38 @@ def main():
     e2e_val = cfg["B"] * world / (float(e2e_ms) * 1e-3)
     clk.__exit__()
 
+    # ---- variant (reported, not the headline): the same masks shipped as uint8 -- bit-identical values after the
+    #      kernel's /255 (what an 8-bit PNG holds before ToTensor, utils/dataloader.py:190), a quarter of the bytes
+    variants = {}
+    if args.mask_dtype == "f32" and not args.no_u8_variant and world == 1:
+        try:
+            inp8 = dict(inp, masks=(inp["masks"] * 255).to(torch.uint8))
+            b8 = region.StepBuffers(cfg["B"], cfg["M"], cfg["C"], cfg["h"], cfg["w"], cfg["H"], cfg["W"], cfg["hp"], cfg["wp"], device=dev,
+                                    mask_dtype=torch.uint8)
+            b8.load(inp8)
+            b8.capture(backward=True, emb_grad=True, warmup=2, **kw)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(args.steps):
+                b8.replay()
+            a1.record()
+            torch.cuda.synchronize()
+            ms8 = a0.elapsed_time(a1) / args.steps
+            host8 = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in inp8.items()}
+            torch.cuda.synchronize()
+            b8.run(host8, **kw)
+            t8 = time.perf_counter()
+            for _ in range(e2e_steps):
+                b8.run(host8, **kw)
+            torch.cuda.synchronize()
+            w8 = (time.perf_counter() - t8) / e2e_steps
+            variants["u8_masks"] = {"value": cfg["B"] / (ms8 * 1e-3), "ms_per_step": ms8, "e2e": {"value": cfg["B"] / w8, "unit": UNIT,
+                                    "h2d_bytes_per_step": b8.h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": w8 * 1e3}}
+            del b8, host8, inp8
+        except Exception as e:   # the variant must never take the headline down with it
+            variants["u8_masks"] = {"error": f"{type(e).__name__}: {e}"}
+
     trace("done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -359,7 +392,7 @@ def main():
                 "data": "synthetic", "config": workload_config(cfg, args), "clocks": clk.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": bufs.h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": float(e2e_ms), "steps": e2e_steps},
-                "gpu_launches": launches, "graphed": graphed, "roofline": roofline, "secondary_kernels": secondary,
+                "gpu_launches": launches, "graphed": graphed, "roofline": roofline, "secondary_kernels": secondary, "variants": variants,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
                 "loss": float(loss.detach())}
         if cpu is not None:

@@ -467,3 +467,43 @@ def test_vailder_offline_order_golden():
     r = ops.val_postprocess(cu(g["pred"]), size=hw, want_hard=True, post_first=True)
     close(r["post"], g["resized"], rtol=1e-5, atol=3e-6)
     assert (r["hard"].cpu().numpy() == g["hard"]).mean() >= 0.999
+
+
+def test_trainer_usage_under_autocast_trains_parameters():
+    """The drop-in functions used exactly like utils/trainer_v3_g.py:51-76 (bf16 autocast, fp32 masks,
+    loss.backward()) on a toy model: gradients reach the parameters and match the ATen port."""
+    from cor_b200 import loss_func as lf
+    from oracle import aten_port as ap
+    torch.manual_seed(3)
+    B = 4
+    enc = torch.nn.Conv2d(3, 64, 3, padding=1).to(dev())
+    head = torch.nn.Conv2d(64, 1, 1).to(dev())
+    proj = torch.nn.Linear(64, 64).to(dev())
+    img = torch.randn(B, 3, 32, 32, device=dev())
+    qmask = (torch.rand(B, 1, 128, 128, device=dev()) > 0.6).float()
+    qmask[1] = 0.0
+
+    def forward(fns):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            emb = enc(img)                                             # bf16 [B,64,32,32]
+            pred = head(emb)                                           # bf16 [B,1,32,32]
+            comb = torch.nn.functional.normalize(proj(emb.mean((2, 3))).float(), dim=-1).unsqueeze(1)
+            target = torch.nn.functional.interpolate(qmask, size=pred.shape[2:], mode="bilinear", align_corners=False)
+            return fns[0](pred, target) + 5 * fns[1](emb, comb, qmask) + 5 * fns[2](emb, comb, qmask)
+
+    params = list(enc.parameters()) + list(head.parameters()) + list(proj.parameters())
+    loss = forward((lf.wbce_with_wiou_loss, lf.fg_feat_similarity_loss, lf.bg_feat_similarity_loss))
+    loss.backward()
+    ours = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    ref = forward((lambda a, b: ap.edge_weighted_seg_loss(a.float(), b), lambda e, c, m: ap.fg_loss(e.float(), c, m),
+                   lambda e, c, m: ap.bg_loss(e.float(), c, m)))
+    ref.backward()
+    close(loss, ref.item(), rtol=2e-3, atol=2e-3)
+    for a, p in zip(ours, params):
+        assert torch.isfinite(a).all()
+        close(a, p.grad.cpu().numpy(), rtol=5e-2, atol=5e-3 * float(p.grad.abs().max()) + 1e-6)
+    with torch.no_grad():
+        v = forward((lf.wbce_with_wiou_loss, lf.fg_feat_similarity_loss, lf.bg_feat_similarity_loss))
+    assert not v.requires_grad and abs(float(v) - float(loss)) < 1e-4
