@@ -11,7 +11,7 @@
 
 namespace cor {
 
-constexpr int kPT = 1024;       // mask pixels per shared-memory tile
+constexpr int kPTBudget = 8192;   // floats of weights in shared memory: the tile covers 8192 / RT mask pixels
 constexpr int kWarps = 8;
 constexpr int kCPW = 2;         // channels per warp per pass (weight registers reused across them)
 constexpr int kCPB = kWarps * kCPW;
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kWarps * 32) pool_stream_kernel(const TF* __re
                                                                   long long ldw, int C, int P, int R, int transform,
                                                                   int vec_ok, float* __restrict__ fg_sum,
                                                                   float* __restrict__ bg_sum) {
+  constexpr int kPT = kPTBudget / RT;   // RT=1 (the reference's single mask): the whole 64x64 map in one tile
   __shared__ __align__(16) float ws[RT][kPT];
   const int b = blockIdx.y, rbase = blockIdx.z * RT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,28 +76,39 @@ __global__ void __launch_bounds__(kWarps * 32) pool_stream_kernel(const TF* __re
     if (c0 >= C) continue;
     if (vec_ok) {
       const int nvec = pt / VE;
-      for (int v = lane; v < nvec; v += 32) {
-        float f[kCPW][VE];
+      constexpr int kU = (RT <= 2) ? 4 : 1;      // vectors in flight per lane and channel (small RT: latency-bound)
+      for (int v0 = lane; v0 < nvec; v0 += 32 * kU) {
+        float f[kU][kCPW][VE];
 #pragma unroll
-        for (int k = 0; k < kCPW; ++k) {
-          uint4 raw = ld_stream16(reinterpret_cast<const uint4*>(frow[k] + p0) + v);
-          FeatVec<TF>::unpack(raw, f[k]);
-        }
+        for (int u = 0; u < kU; ++u)
 #pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          float wv[VE];
-#pragma unroll
-          for (int q = 0; q < VE / 4; ++q) {
-            float4 t = *reinterpret_cast<const float4*>(&ws[r][v * VE + q * 4]);
-            wv[q * 4 + 0] = t.x; wv[q * 4 + 1] = t.y; wv[q * 4 + 2] = t.z; wv[q * 4 + 3] = t.w;
+          for (int k = 0; k < kCPW; ++k) {
+            const int v = v0 + 32 * u;
+            if (v < nvec) {
+              uint4 raw = ld_stream16(reinterpret_cast<const uint4*>(frow[k] + p0) + v);
+              FeatVec<TF>::unpack(raw, f[u][k]);
+            }
           }
 #pragma unroll
-          for (int k = 0; k < kCPW; ++k)
+        for (int u = 0; u < kU; ++u) {
+          const int v = v0 + 32 * u;
+          if (v >= nvec) break;
 #pragma unroll
-            for (int e = 0; e < VE; ++e) {
-              afg[k][r] = fmaf(f[k][e], wv[e], afg[k][r]);
-              if (PAIR) abg[k][r] = fmaf(f[k][e], 1.f - wv[e], abg[k][r]);
+          for (int r = 0; r < RT; ++r) {
+            float wv[VE];
+#pragma unroll
+            for (int q = 0; q < VE / 4; ++q) {
+              float4 t = *reinterpret_cast<const float4*>(&ws[r][v * VE + q * 4]);
+              wv[q * 4 + 0] = t.x; wv[q * 4 + 1] = t.y; wv[q * 4 + 2] = t.z; wv[q * 4 + 3] = t.w;
             }
+#pragma unroll
+            for (int k = 0; k < kCPW; ++k)
+#pragma unroll
+              for (int e = 0; e < VE; ++e) {
+                afg[k][r] = fmaf(f[u][k][e], wv[e], afg[k][r]);
+                if (PAIR) abg[k][r] = fmaf(f[u][k][e], 1.f - wv[e], abg[k][r]);
+              }
+          }
         }
       }
       // pt is a multiple of VE whenever vec_ok (P % VE == 0 and kPT % VE == 0)

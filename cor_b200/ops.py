@@ -111,21 +111,27 @@ class RegionPool:
 _umma_w_cache = {}
 
 
-def _umma_weight_buffer(dev, B, Rp, R, P):
-    key = (dev.index, B, Rp, R, P)
+def _umma_weight_buffer(dev, B, Rp, R, P, ones_row=True):
+    """Cached bf16 weight operand [B, Rp, P] of the tensor-core pooling GEMM: rows < R are rewritten by
+    mask_prep every call, padding rows stay zero, and (with ``ones_row``) row R is all ones so that its
+    pooled sum is sum_p F -- the background by subtraction."""
+    key = (dev.index, B, Rp, R, P, bool(ones_row))
     buf = _umma_w_cache.get(key)
     if buf is None:
         if len(_umma_w_cache) > 8:
             _umma_w_cache.clear()
         buf = torch.zeros((B, Rp, P), dtype=torch.bfloat16, device=dev)
-        buf[:, R, :] = 1.0            # ones row: its pooled sum is sum_p F (background by subtraction)
+        if ones_row:
+            buf[:, R, :] = 1.0
         _umma_w_cache[key] = buf
     return buf
 
 
-def umma_pool_eligible(feat: torch.Tensor, R: int, P: int, transform: int, group: int) -> bool:
+def umma_pool_eligible(feat: torch.Tensor, R: int, P: int, transform: int, group: int, pair: bool = True) -> bool:
+    """Shapes the tcgen05 pooling GEMM serves: bf16 features, 16 <= R, R (+1 ones row when the background
+    is wanted) <= 256 (UMMA N), whole 64-pixel K blocks and 128-channel M tiles."""
     C = feat.shape[1]
-    return (feat.dtype == torch.bfloat16 and R >= 16 and R + 1 <= 256 and P % 64 == 0 and C % 128 == 0
+    return (feat.dtype == torch.bfloat16 and R >= 16 and R + (1 if pair else 0) <= 256 and P % 64 == 0 and C % 128 == 0
             and transform in (W_PLAIN, W_CLAMP) and group == 1)
 
 
@@ -143,9 +149,9 @@ class _RegionPoolFn(torch.autograd.Function):
             raise CorError(f"region_pool: R={R} not divisible by group={group}")
         flat = masks.reshape(B * R, masks.shape[2], masks.shape[3])
         need_w32 = True
-        use_umma = engine == "umma" or (engine == "auto" and umma_pool_eligible(feat_c, R, P, transform, group))
-        if use_umma and not umma_pool_eligible(feat_c, R, P, transform, group):
-            raise CorError("region_pool: engine='umma' needs bf16 features, 16 <= R <= 255, P % 64 == 0, C % 128 == 0")
+        use_umma = engine == "umma" or (engine == "auto" and umma_pool_eligible(feat_c, R, P, transform, group, pair))
+        if use_umma and not umma_pool_eligible(feat_c, R, P, transform, group, pair):
+            raise CorError("region_pool: engine='umma' needs bf16 features, 16 <= R <= 256 (255 with background rows), P % 64 == 0, C % 128 == 0")
         rows_out = B * R // group
         fg = torch.empty((rows_out, Cc), dtype=torch.float32, device=dev)
         bg = torch.empty((rows_out, Cc), dtype=torch.float32, device=dev) if pair else None
@@ -154,8 +160,8 @@ class _RegionPoolFn(torch.autograd.Function):
         inv_bg = torch.empty((rows_out,), dtype=torch.float32, device=dev) if pair else None
         lib = L.load()
         if use_umma:
-            Rp = (R + 1 + 15) // 16 * 16
-            w16 = _umma_weight_buffer(dev, B, Rp, R, P)
+            Rp = (R + (1 if pair else 0) + 15) // 16 * 16
+            w16 = _umma_weight_buffer(dev, B, Rp, R, P, ones_row=pair)
             need_w32 = feat.requires_grad      # backward runs on the fp32 weights
             w32, stats = mask_prep(flat, (h, w), transform, want_f32=need_w32, bf16_out=w16, group=R, group_stride=Rp * P,
                                    mask_scale=mask_scale)

@@ -255,7 +255,7 @@ class _FusedStepFn(torch.autograd.Function):
 def _fused_ok(emb, masks, pool_engine):
     B, M = masks.shape[:2]
     P = emb.shape[2] * emb.shape[3]
-    return pool_engine in ("auto", "umma") and ops.umma_pool_eligible(emb, M, P, ops.W_CLAMP, 1) and emb.shape[1] % 8 == 0
+    return pool_engine in ("auto", "umma") and ops.umma_pool_eligible(emb, M, P, ops.W_CLAMP, 1, True) and emb.shape[1] % 8 == 0
 
 
 def region_step(pred: torch.Tensor, emb: torch.Tensor, comb: torch.Tensor, masks: torch.Tensor, *, tau: float = 0.07,

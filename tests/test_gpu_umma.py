@@ -49,6 +49,19 @@ def test_pool_umma_vs_oracle_and_stream(shape):
     assert torch.equal(pu.fg, pu2.fg) and torch.equal(pu.bg, pu2.bg)
 
 
+def test_pool_umma_256_masks_foreground_only():
+    """The sweep's upper end (256 masks per image): all 256 UMMA N columns are masks when no background
+    rows are asked for."""
+    from cor_b200 import ops, synth
+    from oracle import np_oracle as no
+    d = synth.make_triplets(49, B=1, M=256, C=128, h=16, w=16, H=32, W=32, hp=8, wp=8, degenerate=False)
+    emb16 = torch.from_numpy(d["emb"]).bfloat16()
+    p = ops.region_pool(emb16.to(dev()), cu(d["masks"]), transform=ops.W_CLAMP, normalize=True, pair=False, engine="umma")
+    close(p.fg, no.multi_mask_pool(emb16.float().numpy(), d["masks"]), rtol=1e-3, atol=1e-3)
+    with pytest.raises(Exception):
+        ops.region_pool(emb16.to(dev()), cu(d["masks"]), transform=ops.W_CLAMP, normalize=True, pair=True, engine="umma")
+
+
 def test_pool_umma_unnormalised_sums_hard_masks_exact_weights():
     """Hard masks at 4x scale resample to {0,.25,.5,.75,1}: exact in bf16, so with bf16 features the
     tensor-core sums equal the fp32 streaming sums up to accumulation order."""
