@@ -19,13 +19,15 @@
 //
 // Warp roles (320 threads): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue
 // (warp w reads TMEM lane quarter w % 4 of half (w - 2) / 4).
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace cor {
 
 using namespace umma;
 
-constexpr int kSimStages = 5;
+constexpr int kSimMaxStages = 6;                 // ring depth (A/B on B200: 4, 6 and 10 stages time the same; 6 leaves margin)
 constexpr int kSimHalf = 128;                    // queries per MMA (UMMA M)
 constexpr int kSimBM = 2 * kSimHalf;             // queries per CTA
 constexpr int kSimBN = 128;                      // regions per tile (UMMA N)
@@ -35,19 +37,19 @@ constexpr int kSimBBytes = kSimBN * kSimBK * 2;    // 16 KB: one stage of region
 constexpr int kSimMaxKB = 4;                       // D <= 256
 
 struct SimSmemTail {
-  uint64_t qfull, full[kSimStages], empty[kSimStages], acc_full[2], acc_empty[2];
+  uint64_t qfull, full[kSimMaxStages], empty[kSimMaxStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
 // part layout (shared with the streaming producer's combine kernel): [qtile][gridDim.x][kSimBM][2]
 __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmR,
-                                                          int Nr, int Nq, int nkb, float inv_tau, float* __restrict__ S,
-                                                          float* __restrict__ part) {
+                                                          int Nr, int Nq, int nkb, int nstages, int q_slots, float inv_tau,
+                                                          float* __restrict__ S, float* __restrict__ part) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   uint8_t* q_smem = base;                                                   // [half][kb] x 16 KB
-  uint8_t* r_smem = base + 2 * kSimMaxKB * kSimABytes;                      // kSimStages x 16 KB
-  SimSmemTail* tail = reinterpret_cast<SimSmemTail*>(r_smem + kSimStages * kSimBBytes);
+  uint8_t* r_smem = base + (size_t)q_slots * kSimABytes;                    // nstages x 16 KB
+  SimSmemTail* tail = reinterpret_cast<SimSmemTail*>(r_smem + (size_t)nstages * kSimBBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.y * kSimBM;
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmR);
     mbar_init(&tail->qfull, 1);
-    for (int i = 0; i < kSimStages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], 1); }
+    for (int i = 0; i < nstages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tail->acc_full[i], 1); mbar_init(&tail->acc_empty[i], 8); }
     fence_barrier_init();
   }
@@ -73,12 +75,12 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
       mbar_expect_tx(&tail->qfull, (uint32_t)(nhalf * nkb * kSimABytes));
       for (int hf = 0; hf < nhalf; ++hf)
         for (int kb = 0; kb < nkb; ++kb)
-          tma_load_2d(q_smem + (hf * kSimMaxKB + kb) * kSimABytes, &tmQ, &tail->qfull, kb * kSimBK, q0 + hf * kSimHalf, kEvictLast);
+          tma_load_2d(q_smem + (hf * nkb + kb) * kSimABytes, &tmQ, &tail->qfull, kb * kSimBK, q0 + hf * kSimHalf, kEvictLast);
       int it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % kSimStages;
-          mbar_wait(&tail->empty[st], ((it / kSimStages) & 1) ^ 1);
+          const int st = it % nstages;
+          mbar_wait(&tail->empty[st], ((it / nstages) & 1) ^ 1);
           mbar_expect_tx(&tail->full[st], kSimBBytes);
           tma_load_2d(r_smem + st * kSimBBytes, &tmR, &tail->full[st], kb * kSimBK, t * kSimBN, gridDim.y > 1 ? kEvictLast : kEvictFirst);
         }
@@ -94,12 +96,12 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
         mbar_wait(&tail->acc_empty[buf], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % kSimStages;
-          mbar_wait(&tail->full[st], (it / kSimStages) & 1);
+          const int st = it % nstages;
+          mbar_wait(&tail->full[st], (it / nstages) & 1);
           tc_fence_after();
           const uint64_t db = make_desc_sw128(smem_u32(r_smem + st * kSimBBytes));
           for (int hf = 0; hf < nhalf; ++hf) {
-            const uint64_t da = make_desc_sw128(smem_u32(q_smem + (hf * kSimMaxKB + kb) * kSimABytes));
+            const uint64_t da = make_desc_sw128(smem_u32(q_smem + (hf * nkb + kb) * kSimABytes));
             const uint32_t d_addr = tmem + (uint32_t)((buf * 2 + hf) * kSimBN);
 #pragma unroll
             for (int k = 0; k < kSimBK / 16; ++k) mma_bf16_ss(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
@@ -213,11 +215,17 @@ extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr
   int gx = sm_count() / qtiles;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
-  const size_t smem = (size_t)2 * kSimMaxKB * kSimABytes + (size_t)kSimStages * kSimBBytes + sizeof(SimSmemTail) + 1024;
+  // queries take nhalf * nkb 16-KB slots; the ring gets up to kSimMaxStages of the remaining 16-KB slots
+  const int nkb = D / kSimBK;
+  const int q_slots = (Nq > kSimHalf ? 2 : 1) * nkb;
+  int nstages = (int)((227 * 1024 - sizeof(SimSmemTail) - 1024) / kSimBBytes) - q_slots;
+  if (nstages > kSimMaxStages) nstages = kSimMaxStages;
+  if (const char* e = getenv("COR_SIM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= nstages) nstages = v; }   // A/B knob
+  const size_t smem = (size_t)q_slots * kSimABytes + (size_t)nstages * kSimBBytes + sizeof(SimSmemTail) + 1024;
   cudaStream_t st = as_stream(stream);
   COR_CUDA(cudaFuncSetAttribute(sim_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* part = lse ? (float*)work : nullptr;
-  sim_umma_kernel<<<dim3(gx, qtiles), 320, smem, st>>>(tmQ, tmR, Nr, Nq, D / kSimBK, inv_tau, S, part);
+  sim_umma_kernel<<<dim3(gx, qtiles), 320, smem, st>>>(tmQ, tmR, Nr, Nq, nkb, nstages, q_slots, inv_tau, S, part);
   rc = check_launch("sim_umma_kernel");
   if (rc || !lse) return rc;
   // inactive query rows of a half-empty last tile publish nothing; the combine only reads rows < Nq
