@@ -43,7 +43,7 @@ struct SimSmemTail {
 
 // part layout (shared with the streaming producer's combine kernel): [qtile][gridDim.x][kSimBM][2]
 __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmR,
-                                                          int Nr, int Nq, int nkb, int nstages, int q_slots, float inv_tau,
+                                                          int Nr, int Nq, int nkb, int nstages, int q_slots, int cl, float inv_tau,
                                                           float* __restrict__ S, float* __restrict__ part) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
@@ -60,15 +60,20 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
     prefetch_tmap(&tmQ);
     prefetch_tmap(&tmR);
     mbar_init(&tail->qfull, 1);
-    for (int i = 0; i < nstages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], 1); }
+    // a stage is released once the MMAs of ALL cl CTAs of the cluster have read it (every CTA's TMA slice lands in all of them)
+    for (int i = 0; i < nstages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], (uint32_t)cl); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tail->acc_full[i], 1); mbar_init(&tail->acc_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tail->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync();       // every CTA's barriers are initialised before any peer multicasts into them
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
+  const uint32_t crank = cl > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
+  const int slice_rows = kSimBN / cl;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -82,7 +87,11 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
           const int st = it % nstages;
           mbar_wait(&tail->empty[st], ((it / nstages) & 1) ^ 1);
           mbar_expect_tx(&tail->full[st], kSimBBytes);
-          tma_load_2d(r_smem + st * kSimBBytes, &tmR, &tail->full[st], kb * kSimBK, t * kSimBN, gridDim.y > 1 ? kEvictLast : kEvictFirst);
+          if (cl > 1)   // this CTA fetches rows [crank*slice, +slice) of the stage and multicasts them to the whole cluster
+            tma_load_2d_mc(r_smem + st * kSimBBytes + crank * slice_rows * (kSimBK * 2), &tmR, &tail->full[st], kb * kSimBK,
+                           t * kSimBN + (int)crank * slice_rows, cmask, gridDim.y > (unsigned)cl ? kEvictLast : kEvictFirst);
+          else
+            tma_load_2d(r_smem + st * kSimBBytes, &tmR, &tail->full[st], kb * kSimBK, t * kSimBN, gridDim.y > 1 ? kEvictLast : kEvictFirst);
         }
       }
     }
@@ -106,7 +115,8 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
 #pragma unroll
             for (int k = 0; k < kSimBK / 16; ++k) mma_bf16_ss(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          mma_commit(&tail->empty[st]);
+          if (cl > 1) mma_commit_mc(&tail->empty[st], cmask);
+          else mma_commit(&tail->empty[st]);
         }
         mma_commit(&tail->acc_full[buf]);
       }
@@ -194,6 +204,7 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync();       // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -206,12 +217,18 @@ extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr
   COR_REQUIRE(regions && queries && (S || lse), "cor_sim_umma_fwd: null pointer");
   COR_REQUIRE(Nr > 0 && Nq > 0 && D % kSimBK == 0 && D >= kSimBK && D <= kSimMaxKB * kSimBK, "cor_sim_umma_fwd: need D in {64,128,192,256} (D=%d)", D);
   COR_REQUIRE(!lse || work, "cor_sim_umma_fwd: lse needs a work buffer");
+  const int qtiles = ceil_div(Nq, kSimBM), ntiles = ceil_div(Nr, kSimBN);
+  // CTAs that walk the same region tiles for different query tiles can form a cluster (along grid.y) and share every
+  // region stage through TMA multicast (L2 -> SM traffic of the region stream / cluster size).  Measured on B200
+  // (profiles/README.md): no gain at cluster 2, -12 % at cluster 4 (only 132 of 148 SMs host whole clusters) -- the
+  // kernel is paced by the TMEM read-out of the S tile, not by L2 -- so the default stays 1; COR_SIM_CLUSTER=2|4 enables it.
+  int cl = 1;
+  if (const char* e = getenv("COR_SIM_CLUSTER")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && qtiles % v == 0) cl = v; }
   CUtensorMap tmQ, tmR;
   int rc = umma::encode_tmap_bf16_2d(&tmQ, queries, (uint64_t)Nq, (uint64_t)D, kSimHalf, kSimBK);
   if (rc) return rc;
-  rc = umma::encode_tmap_bf16_2d(&tmR, regions, (uint64_t)Nr, (uint64_t)D, kSimBN, kSimBK);
+  rc = umma::encode_tmap_bf16_2d(&tmR, regions, (uint64_t)Nr, (uint64_t)D, kSimBN / cl, kSimBK);
   if (rc) return rc;
-  const int qtiles = ceil_div(Nq, kSimBM), ntiles = ceil_div(Nr, kSimBN);
   int gx = sm_count() / qtiles;
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
@@ -225,7 +242,30 @@ extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr
   cudaStream_t st = as_stream(stream);
   COR_CUDA(cudaFuncSetAttribute(sim_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   float* part = lse ? (float*)work : nullptr;
-  sim_umma_kernel<<<dim3(gx, qtiles), 320, smem, st>>>(tmQ, tmR, Nr, Nq, nkb, nstages, q_slots, inv_tau, S, part);
+  const int nkb_arg = nkb;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, qtiles);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)cl;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cl > 1) {
+    // persistent CTAs: every cluster must be resident at once (a GPC may not fit a whole number of clusters)
+    int max_clusters = 0;
+    COR_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, sim_umma_kernel, &cfg));
+    const int per_x = qtiles / cl;
+    if (max_clusters >= per_x && gx > max_clusters / per_x) {
+      gx = max_clusters / per_x;
+      cfg.gridDim = dim3(gx, qtiles);
+    }
+  }
+  COR_CUDA(cudaLaunchKernelEx(&cfg, sim_umma_kernel, tmQ, tmR, Nr, Nq, nkb_arg, nstages, q_slots, cl, inv_tau, S, part));
   rc = check_launch("sim_umma_kernel");
   if (rc || !lse) return rc;
   // inactive query rows of a half-empty last tile publish nothing; the combine only reads rows < Nq
