@@ -82,6 +82,7 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_l2_normalize", i, p, i, i, i, p, p, p, p)
         _sig(lib, "cor_val_post_work_bytes", sz, i, i, i)
         _sig(lib, "cor_val_post", i, p, i, i, i, i, i, i, i, p, p, p, i, f, p, p, p)
+        _sig(lib, "cor_soft_metrics", i, p, p, i, f, i, ll, f, p, p, p)
         if lib.cor_abi_version() != 1:
             raise CorError(f"ABI version mismatch: library {lib.cor_abi_version()}, binding 1")
         _lib = lib

@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) val_write_kernel(const TP* __restrict__ p
 }
 
 // metrics [N][5] = {dice, mae, iou, mdice, miou}, smooth = 1e-5 (trainer_v3_g.py:381-443)
-__global__ void val_metrics_kernel(const double* __restrict__ met_part, int N, int chunks, double total, float* __restrict__ metrics) {
+__global__ void val_metrics_kernel(const double* __restrict__ met_part, int N, int chunks, double total, double s,
+                                   float* __restrict__ metrics) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   double pg = 0, sp = 0, sg = 0, ad = 0;
@@ -139,7 +140,6 @@ __global__ void val_metrics_kernel(const double* __restrict__ met_part, int N, i
     const double* o = met_part + ((long long)n * chunks + c) * 4;
     pg += o[0]; sp += o[1]; sg += o[2]; ad += o[3];
   }
-  const double s = 1e-5;
   const double bp = total - sp, bg = total - sg, bpg = total - sp - sg + pg;   // sums of (1-p), (1-g), (1-p)(1-g)
   const double dice = (2 * pg + s) / (sp + sg + s), dice_b = (2 * bpg + s) / (bp + bg + s);
   const double iou = (pg + s) / (sp + sg - pg + s), iou_b = (bpg + s) / (bp + bg - bpg + s);
@@ -249,6 +249,28 @@ __global__ void __launch_bounds__(256) val_up4_write_kernel(const TP* __restrict
   }
 }
 
+// ---- stand-alone soft metrics (compute_dice / mae / iou / mdice / miou, utils/trainer_v3_g.py:381-443) ----------
+// One pass over (pred, gt): {sum p*g, sum p, sum g, sum |p-g|} per sample -> the five metrics.  HBM-bound.
+template <typename TG>
+__global__ void __launch_bounds__(256) soft_metrics_kernel(const float* __restrict__ pred, const TG* __restrict__ gt, float gscale,
+                                                           long long total, double* __restrict__ met_part) {
+  __shared__ double scratch[4 * 32];
+  const int n = blockIdx.y;
+  const float* p = pred + (long long)n * total;
+  const TG* g = gt + (long long)n * total;
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    const float v = p[o], t = to_f<TG>(g[o]) * gscale;
+    f0 = fmaf(v, t, f0); f1 += v; f2 += t; f3 += fabsf(v - t);
+  }
+  double acc[4] = {f0, f1, f2, f3};
+  block_sum<4>(acc, scratch);
+  if (threadIdx.x == 0) {
+    double* o = met_part + ((long long)n * gridDim.x + blockIdx.x) * 4;
+    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+  }
+}
+
 static int val_chunks(int N, long long total) {
   long long c = ((long long)sm_count() * 8 + N - 1) / N;
   const long long cap = (total + 1023) / 1024;
@@ -297,7 +319,7 @@ extern "C" int cor_val_post(const void* pred, int pred_dtype, int N, int H, int 
 #undef COR_VW4
     rc4 = check_launch("val_up4_write_kernel");
     if (rc4 || !gt) return rc4;
-    val_metrics_kernel<<<ceil_div(N, 128), 128, 0, st>>>(met_part, N, c4, (double)total, metrics);
+    val_metrics_kernel<<<ceil_div(N, 128), 128, 0, st>>>(met_part, N, c4, (double)total, 1e-5, metrics);
     return check_launch("val_metrics_kernel");
   }
   // post_first: the min / max are those of the sigmoid at the logit resolution
@@ -316,6 +338,23 @@ extern "C" int cor_val_post(const void* pred, int pred_dtype, int N, int H, int 
 #undef COR_VW
   rc = check_launch("val_write_kernel");
   if (rc || !gt) return rc;
-  val_metrics_kernel<<<ceil_div(N, 128), 128, 0, st>>>(met_part, N, chunks, (double)total, metrics);
+  val_metrics_kernel<<<ceil_div(N, 128), 128, 0, st>>>(met_part, N, chunks, (double)total, 1e-5, metrics);
+  return check_launch("val_metrics_kernel");
+}
+
+extern "C" int cor_soft_metrics(const float* pred, const void* gt, int gt_dtype, float gt_scale, int N, long long total, float smooth,
+                                float* metrics, void* work, cor_stream_t stream) {
+  COR_REQUIRE(pred && gt && metrics && work, "cor_soft_metrics: null pointer");
+  COR_REQUIRE(N > 0 && N <= 65535 && total > 0, "cor_soft_metrics: bad shape");
+  cudaStream_t st = as_stream(stream);
+  const int chunks = val_chunks(N, total);
+  double* met_part = reinterpret_cast<double*>(work);
+  dim3 grid(chunks, N);
+  if (gt_dtype == COR_F32) soft_metrics_kernel<float><<<grid, 256, 0, st>>>(pred, (const float*)gt, gt_scale, total, met_part);
+  else if (gt_dtype == COR_U8) soft_metrics_kernel<uint8_t><<<grid, 256, 0, st>>>(pred, (const uint8_t*)gt, gt_scale, total, met_part);
+  else COR_REQUIRE(false, "cor_soft_metrics: unsupported gt dtype %d", gt_dtype);
+  int rc = check_launch("soft_metrics_kernel");
+  if (rc) return rc;
+  val_metrics_kernel<<<ceil_div(N, 128), 128, 0, st>>>(met_part, N, chunks, (double)total, (double)smooth, metrics);
   return check_launch("val_metrics_kernel");
 }

@@ -5,6 +5,7 @@ The reference has no plugin registry; its hot path is reached through Python nam
 
   utils.loss_func.{wbce_with_wiou_loss, mask_pooling, fg_feat_similarity_loss, bg_feat_similarity_loss}
   utils.trainer_v3_g.{wbce_with_wiou_loss, fg_feat_similarity_loss, bg_feat_similarity_loss}   (imported by name, :5-9)
+  utils.trainer_v3_g.{compute_dice, compute_mae, compute_iou, compute_mdice, compute_miou}     (val_stage, :233-237)
   lib.support_model.mask_adapter.{MaskedPooling.forward, MaskAdapterPooling.forward}
       -> so SupportBranch(mask_pooling="MaskedPooling"|"MaskAdapterPooling") (lib/support_branch.py:29-40)
          built through build_model_with_query_support_feat(..., mask_pooling=) (lib/build_model.py:14-20,72)
@@ -21,8 +22,10 @@ import torch.nn.functional as F
 
 from . import loss_func as _lf
 from . import mask_adapter as _ma
+from . import metrics as _mt
 
 _LOSS_NAMES = ("wbce_with_wiou_loss", "mask_pooling", "fg_feat_similarity_loss", "bg_feat_similarity_loss")
+_METRIC_NAMES = ("compute_dice", "compute_mae", "compute_iou", "compute_mdice", "compute_miou")
 _saved = {}
 
 
@@ -63,6 +66,10 @@ def install(loss_module="utils.loss_func", trainer_module="utils.trainer_v3_g",
             if hasattr(tm, n):
                 _saved.setdefault((tm.__name__, n), getattr(tm, n))
                 setattr(tm, n, getattr(_lf, n))
+        for n in _METRIC_NAMES:          # val_stage's five soft metrics (trainer_v3_g.py:233-237, :381-443)
+            if hasattr(tm, n):
+                _saved.setdefault((tm.__name__, n), getattr(tm, n))
+                setattr(tm, n, getattr(_mt, n))
         done.append(tm.__name__)
     am = _maybe(adapter_module) if isinstance(adapter_module, str) else adapter_module
     if am is not None:

@@ -30,7 +30,7 @@ _KERNELS_PER_CALL = {
     "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_umma": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
     "cor_fgbg_loss_bwd": 1, "cor_step_combine": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
     "cor_sim_umma_fwd": 2, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
-    "cor_val_post": 3,
+    "cor_val_post": 3, "cor_soft_metrics": 2,
 }
 
 
@@ -537,3 +537,20 @@ def val_postprocess(pred: torch.Tensor, size=None, gt: Optional[torch.Tensor] = 
     _call("cor_val_post", dev, ptr(pc), dtype_code(pc), N, H, W, Ho, Wo, int(post_first), ptr(post), ptr(hard), ptr(gc),
           (dtype_code(gc) if gc is not None else F32), _f(_mask_scale(gc, gt_scale) if gc is not None else 1.0), ptr(metrics), ptr(work))
     return {"post": post, "hard": hard, "metrics": metrics}
+
+
+def soft_metrics(pred: torch.Tensor, gt: torch.Tensor, smooth: float = 1e-5, gt_scale: Optional[float] = None) -> torch.Tensor:
+    """[N,5] = {dice, mae, iou, mdice, miou} of utils/trainer_v3_g.py:381-443 in one pass over (pred, gt)."""
+    dev = require_cuda(pred, gt)
+    if pred.shape != gt.shape:
+        raise CorError(f"Shape mismatch: pred {tuple(pred.shape)} vs gt {tuple(gt.shape)}")
+    N = pred.shape[0]
+    pc = pred.reshape(N, -1).float().contiguous()
+    gc = gt.reshape(N, -1)
+    gc = (gc if gc.dtype in (torch.float32, torch.uint8) else gc.float()).contiguous()
+    lib = L.load()
+    out = torch.empty((N, 5), dtype=torch.float32, device=dev)
+    work = _work(lib.cor_val_post_work_bytes(N, 1, 1), dev)
+    _call("cor_soft_metrics", dev, ptr(pc), ptr(gc), dtype_code(gc), _f(_mask_scale(gc, gt_scale)), N, _ll(pc.shape[1]), _f(smooth),
+          ptr(out), ptr(work))
+    return out

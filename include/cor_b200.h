@@ -210,6 +210,11 @@ int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, 
                  uint8_t* hard, const void* gt, int gt_dtype, float gt_scale, float* metrics, void* work,
                  cor_stream_t stream);
 
+/* Soft metrics of utils/trainer_v3_g.py:381-443 on an already post-processed map: pred [N, total] f32, gt [N, total]
+ * f32 / u8 -> metrics [N,5] {dice, mae, iou, mdice, miou}; work: cor_val_post_work_bytes(N, ...) bytes. */
+int cor_soft_metrics(const float* pred, const void* gt, int gt_dtype, float gt_scale, int N, long long total,
+                     float smooth, float* metrics, void* work, cor_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,9 @@ def test_dropin_signatures_match_the_reference():
     assert sig(lf.mask_pooling) == ["embeddings", "mask"]
     assert sig(lf.fg_feat_similarity_loss) == ["query_image_embeddings", "comb_support_feat", "query_mask"]
     assert sig(lf.bg_feat_similarity_loss) == ["query_image_embeddings", "comb_support_feat", "query_mask"]
+    from cor_b200 import metrics as mt
+    assert sig(mt.compute_dice) == ["pred", "gt", "smooth"] and sig(mt.compute_mae) == ["pred", "gt"]
+    assert sig(mt.compute_miou) == ["pred", "gt", "smooth"]
     assert sig(ma.MaskedPooling.forward) == ["self", "clip_feature", "mask"]
     assert sig(ma.MaskAdapterPooling.forward) == ["self", "clip_feature", "mask"]
     assert sig(ma.MaskAdapterPooling.__init__) == ["self", "x_in_channel", "mask_adatpet_network_in_channel",

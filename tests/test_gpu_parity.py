@@ -507,3 +507,21 @@ def test_trainer_usage_under_autocast_trains_parameters():
     with torch.no_grad():
         v = forward((lf.wbce_with_wiou_loss, lf.fg_feat_similarity_loss, lf.bg_feat_similarity_loss))
     assert not v.requires_grad and abs(float(v) - float(loss)) < 1e-4
+
+
+def test_drop_in_metric_functions_golden():
+    """compute_dice / mae / iou / mdice / miou (trainer_v3_g.py:381-443) through cor_b200.metrics: one pass serves
+    all five calls, values equal the reference's."""
+    from cor_b200 import metrics as mt
+    from cor_b200 import ops
+    g = load_golden("val_post")
+    pred, gt = cu(g["post_up"]), cu(g["gt"])
+    n0 = ops.LAUNCHES["count"]
+    res = {"dice": mt.compute_dice(pred, gt), "mae": mt.compute_mae(pred, gt), "iou": mt.compute_iou(pred, gt),
+           "mdice": mt.compute_mdice(pred, gt), "miou": mt.compute_miou(pred, gt)}
+    assert ops.LAUNCHES["count"] - n0 == 2, "five metric calls on the same tensors must share one pass"
+    for k, v in res.items():
+        assert v.shape == (2,)
+        close(v, g[k], rtol=1e-5, atol=1e-7)
+    close(mt.compute_dice(pred, gt, smooth=1.0), (2 * (g["post_up"] * g["gt"]).reshape(2, -1).sum(1) + 1.0) /
+          (g["post_up"].reshape(2, -1).sum(1) + g["gt"].reshape(2, -1).sum(1) + 1.0), rtol=1e-5, atol=1e-7)
