@@ -193,3 +193,44 @@ def test_fused_step_equals_modular_ops(bg_mode):
     close(pa, pb, rtol=1e-5, atol=1e-9)
     close(ca, cb, rtol=1e-4, atol=1e-6)
     close(ea, eb, rtol=2e-2, atol=2e-3 * float(eb.abs().max()))
+
+
+def test_full_size_config2_tensor_core_step_vs_exact_engines():
+    """BASELINE config 2 at full size (16 triplets x 64 masks of 1024^2, bf16 features): the fused tensor-core
+    step against the composition of the exact fp32 streaming engines -- loss parts, region rows, gradients --
+    plus size-independent properties (unit rows, zero rows for empty masks, top-1 of each query among its own
+    image's regions being reproducible)."""
+    from cor_b200 import region
+    B, M = 16, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    emb = torch.randn(B, 256, 64, 64, device=dev(), generator=g).bfloat16()
+    comb = torch.nn.functional.normalize(torch.randn(B, 1, 256, device=dev(), generator=g), dim=-1)
+    pred = (2 * torch.randn(B, 1, 256, 256, device=dev(), generator=g)).bfloat16()
+    masks = torch.zeros(B, M, 1024, 1024, device=dev())
+    for m in range(M):
+        y0, x0 = (53 * m) % 640, (97 * m) % 640
+        masks[:, m, y0:y0 + 96 + 4 * m, x0:x0 + 128 + 3 * m] = 1.0
+    masks[2, 0] = 0.0                       # empty GT mask -> invalid fg sample
+    masks[5, 9] = 0.0
+    res = []
+    for fused, pe, se in ((True, "umma", "auto"), (False, "stream", "stream")):
+        p = pred.clone().requires_grad_(True)
+        c = comb.clone().requires_grad_(True)
+        e = emb.clone().requires_grad_(True)
+        o = region.region_step(p, e, c, masks, tau=0.07, gather=False, pool_engine=pe, sim_engine=se, fused=fused)
+        o.loss.backward()
+        res.append((o, p.grad.float(), c.grad.float(), e.grad.float()))
+    (a, pa, ca, ea), (b, pb, cb, eb) = res
+    for k in ("loss", "seg", "fg", "bg", "nce"):
+        close(getattr(a, k), getattr(b, k), rtol=1e-3, atol=1e-3)
+    close(a.regions, b.regions, rtol=1e-3, atol=1e-3)
+    close(pa, pb, rtol=1e-4, atol=1e-9)
+    close(ca, cb, rtol=2e-2, atol=2e-3 * float(cb.abs().max()))
+    assert float((ea - eb).norm() / eb.norm()) < 2e-2
+    n = a.regions.norm(dim=-1)
+    assert float(a.regions[5, 9].abs().max()) == 0.0 and float(a.regions[2, 0].abs().max()) == 0.0
+    ok = n > 0
+    assert torch.allclose(n[ok], torch.ones_like(n[ok]), atol=2e-3)
+    ia, _ = region.topk_regions(a.regions.reshape(B * M, 256), comb.reshape(B, 256), 5)
+    ib, _ = region.topk_regions(a.regions.reshape(B * M, 256), comb.reshape(B, 256), 5, engine="stream")
+    assert torch.equal(ia, ib)
