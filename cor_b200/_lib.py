@@ -83,6 +83,19 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_val_post_work_bytes", sz, i, i, i)
         _sig(lib, "cor_val_post", i, p, i, i, i, i, i, i, i, p, p, p, i, f, p, p, p)
         _sig(lib, "cor_soft_metrics", i, p, p, i, f, i, ll, f, p, p, p)
+        pp = C.POINTER(C.c_void_p)
+        _sig(lib, "cor_peer_max_world", i)
+        _sig(lib, "cor_peer_flag_bytes", sz)
+        _sig(lib, "cor_peer_state_bytes", sz)
+        _sig(lib, "cor_peer_alloc", i, i, sz, pp)
+        _sig(lib, "cor_peer_free", i, p)
+        _sig(lib, "cor_peer_export", i, p, C.c_char_p)
+        _sig(lib, "cor_peer_open", i, i, C.c_char_p, pp)
+        _sig(lib, "cor_peer_close", i, p)
+        _sig(lib, "cor_peer_signal", i, p, p, i, i, i, p)
+        _sig(lib, "cor_peer_wait_exit", i, p, p, i, i, i, p)
+        _sig(lib, "cor_peer_gather_rows", i, p, p, ll, p, p, i, i, i, p)
+        _sig(lib, "cor_peer_reduce_rows", i, p, p, ll, p, p, i, i, i, p)
         if lib.cor_abi_version() != 1:
             raise CorError(f"ABI version mismatch: library {lib.cor_abi_version()}, binding 1")
         _lib = lib

@@ -16,6 +16,7 @@ import torch
 
 from . import dist as cdist
 from . import ops
+from . import peer
 from ._lib import CorError
 
 __all__ = ["pool_regions", "region_query_similarity", "region_infonce_loss", "topk_regions", "region_step", "RegionStepOut",
@@ -113,11 +114,18 @@ class _FusedStepFn(torch.autograd.Function):
         part = torch.empty((ks, B, Rp, Cc), **f32)
         call("cor_pool_umma_fwd", dev, ptr(emb_c), ptr(w16), B, Cc, P, Rp, ptr(part))
         fg = torch.empty((B * M, Cc), **f32)
-        fg16 = torch.empty((B * M, Cc), dtype=torch.bfloat16, device=dev)
+        # multi-GPU: the bf16 rows land directly in this rank's peer-mapped buffer (cor_b200/peer.py), else in a local one
+        rank, ws = cdist.world()
+        px = peer.get_exchange(B * M, Cc, dev) if (gather and ws > 1 and os.environ.get("COR_STEP_BWD", "reduce_scatter") != "local") else None
+        fg16 = px.pub if px is not None else torch.empty((B * M, Cc), dtype=torch.bfloat16, device=dev)
+        if px is not None:
+            px.before_produce(0)
         inv_fg = torch.empty((B * M,), **f32)
         split = B * Rp * Cc
         call("cor_rows_finalize", dev, ptr(part), M, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, 3:]), 4, _f(1e-8), B * M, Cc, 1, 1,
              None, _f(0.0), ptr(fg), ptr(fg16), ptr(inv_fg))
+        if px is not None:
+            px.signal(0)                     # the bg rows, fg/bg loss and segmentation loss below hide the rank skew
         bg = torch.empty((B, Cc), **f32)
         inv_bg = torch.empty((B,), **f32)
         call("cor_rows_finalize", dev, ptr(part), 1, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, 3:]), 4 * M, _f(1e-8), B, Cc, 1, 1,
@@ -145,7 +153,6 @@ class _FusedStepFn(torch.autograd.Function):
              ptr(work))
         # 6. InfoNCE of every composed query against all (gathered) regions
         q16 = comb_c.to(torch.bfloat16)
-        rank, ws = cdist.world()
         n_local = B * M
         inv_tau = 1.0 / float(tau)
         # A/B on one 8xB200 box (profiles/README.md): reduce-scatter of the region gradient 0.951 ms/step, collective-free
@@ -153,7 +160,10 @@ class _FusedStepFn(torch.autograd.Function):
         local_bwd = os.environ.get("COR_STEP_BWD", "reduce_scatter") == "local"
         if gather and ws > 1:
             r16 = torch.empty((ws * n_local, Cc), dtype=torch.bfloat16, device=dev)
-            torch.distributed.all_gather_into_tensor(r16, fg16)
+            if px is not None:
+                px.gather(r16)               # our own pull-over-NVLink kernel: no NCCL on the data path
+            else:
+                torch.distributed.all_gather_into_tensor(r16, fg16)
             offset = rank * n_local
             if local_bwd:
                 # A second small all-gather (the queries) replaces the backward's reduce-scatter: every rank scores
@@ -182,6 +192,7 @@ class _FusedStepFn(torch.autograd.Function):
                               fg16, q_all, lse_all, tgt_all)
         ctx.cfg = (B, M, Cc, h, w, float(inv_tau), float(nce_weight), int(bg_mode), float(w_fg), float(w_bg), ws, offset, n_local,
                    pred.dtype, emb.dtype, comb.dtype, tuple(comb.shape), need_pred, need_emb, comb.requires_grad)
+        ctx.px = px
         ctx.mark_non_differentiable(fg, out8, out4, nce)
         ctx.set_materialize_grads(False)     # no zero-filled gradients for the auxiliary outputs
         return loss[0], out8, out4, nce, fg
@@ -202,12 +213,18 @@ class _FusedStepFn(torch.autograd.Function):
             return (None,) * 11
         g = g_loss.reshape(1).float().contiguous()
         g_pred = g_emb = g_comb = None
-        if need_pred:
+        def seg_bwd():
+            if not need_pred:
+                return None
             N, H, W = t_save.shape
-            g_pred = torch.empty_like(pred_c)
+            gp = torch.empty_like(pred_c)
             call("cor_seg_loss_bwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _f(1.0), _f(1.0),
-                 ptr(g), ptr(g_pred), L.dtype_code(g_pred))
-            g_pred = g_pred.to(pred_dt)
+                 ptr(g), ptr(gp), L.dtype_code(gp))
+            return gp.to(pred_dt)
+
+        px = ctx.px
+        if px is None:
+            g_pred = seg_bwd()
         # InfoNCE backward first: it WRITES g_regions (this rank's rows) and g_queries ...
         Nr = r16.shape[0]
         g_regions = torch.empty((n_local, Cc), **f32)
@@ -221,10 +238,17 @@ class _FusedStepFn(torch.autograd.Function):
             call("cor_infonce_bwd", dev, ptr(fg16), ptr(q_all), ptr(tgt_all), ptr(lse_all), n_local, ws * B, Cc, _f(inv_tau), ptr(g),
                  _f(float(ws) * nce_weight), ptr(g_regions), None, None)
         elif ws > 1:
-            g_all = torch.empty((Nr, Cc), **f32)
+            if px is not None:
+                px.before_produce(1)
+            g_all = px.gall if px is not None else torch.empty((Nr, Cc), **f32)
             call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g), _f(nce_weight),
                  ptr(g_all), ptr(g_q), ptr(work))
-            torch.distributed.reduce_scatter_tensor(g_regions, g_all, op=torch.distributed.ReduceOp.SUM)
+            if px is not None:
+                px.signal(1)
+                g_pred = seg_bwd()           # independent work between the signal and the pull hides the rank skew
+                px.reduce(g_regions)         # fixed rank order: bit-identical from run to run
+            else:
+                torch.distributed.reduce_scatter_tensor(g_regions, g_all, op=torch.distributed.ReduceOp.SUM)
         else:
             call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g), _f(nce_weight),
                  ptr(g_regions), ptr(g_q), ptr(work))

@@ -215,6 +215,40 @@ int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, 
 int cor_soft_metrics(const float* pred, const void* gt, int gt_dtype, float gt_scale, int N, long long total,
                      float smooth, float* metrics, void* work, cor_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * (e) Multi-GPU exchange over NVLink peer memory (one process per GPU, one node) - the B200-native replacement of
+ * the all-gather of the region rows and the reduce-scatter of their gradient around the similarity stage
+ * (the reference gathers nothing: its loss is per-sample, utils/trainer_v3_g.py:67-73, and its
+ * multi-GPU plumbing is accelerate/DDP, utils/trainer_v3_g.py:46-57).
+ *   cor_peer_alloc/free: a zero-filled cudaMalloc region on `device`; cor_peer_export: its 64-byte CUDA IPC handle;
+ *   cor_peer_open/close: map a peer's region into this process (peer access enabled lazily).
+ *   flags: every rank sets aside cor_peer_flag_bytes() of its region (zeroed), peers signal into it; state:
+ *   cor_peer_state_bytes() of LOCAL zeroed memory (epoch + CTA counter per channel).
+ *   peer_src / peer_flags: DEVICE arrays [world] of pointers (entry `rank` = the local buffer).
+ *   cor_peer_gather_rows:  all[p*bytes : (p+1)*bytes] = peer_src[p][0 : bytes]   for every rank p
+ *   cor_peer_reduce_rows:  out[i] = sum_p peer_src[p][rank*floats + i], p ascending (deterministic)
+ *   cor_peer_signal:    "my buffer for the next epoch of `channel` is ready" - one tiny CTA right after the producer
+ *                       kernel; exactly one per exchange, BEFORE it (what runs in between hides the rank skew)
+ *   cor_peer_wait_exit: "every peer has finished reading what my last exchange on `channel` published" - needed
+ *                       before the producer only when no exchange on the other channel ran since (cor_b200/peer.py)
+ *   The exchanges wait for all peers' signal, pull, and post their own exit flag.  Epochs live in device memory:
+ *   graph-capturable; every rank must issue the same sequence; a wait that exceeds ~20 s traps instead of hanging.
+ * ---------------------------------------------------------------------------------------------- */
+int cor_peer_max_world(void);
+size_t cor_peer_flag_bytes(void);
+size_t cor_peer_state_bytes(void);
+int cor_peer_alloc(int device, size_t bytes, void** ptr);
+int cor_peer_free(void* ptr);
+int cor_peer_export(void* ptr, unsigned char* handle64);
+int cor_peer_open(int device, const unsigned char* handle64, void** ptr);
+int cor_peer_close(void* ptr);
+int cor_peer_signal(void* const* peer_flags, void* state, int rank, int world, int channel, cor_stream_t stream);
+int cor_peer_wait_exit(void* const* peer_flags, void* state, int rank, int world, int channel, cor_stream_t stream);
+int cor_peer_gather_rows(const void* const* peer_src, void* all, long long bytes_per_rank, void* const* peer_flags, void* state,
+                         int rank, int world, int channel, cor_stream_t stream);
+int cor_peer_reduce_rows(const void* const* peer_src, float* out, long long floats_per_rank, void* const* peer_flags, void* state,
+                         int rank, int world, int channel, cor_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
