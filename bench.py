@@ -291,10 +291,18 @@ def main():
 
     trace("events pass")
     # ---- per-kernel durations: the same K steps once more, eager, with CUDA events around every C-ABI call
+    #      (single stream: COR_STEP_OVERLAP=0 keeps the segmentation-loss branch from running underneath the kernels being
+    #      timed, so every duration is that kernel alone; the timed region above runs with the branch overlapped)
     ops.TIMING["events"] = {}
+    prev_overlap = os.environ.get("COR_STEP_OVERLAP")
+    os.environ["COR_STEP_OVERLAP"] = "0"
     for _ in range(args.steps):
         bufs._step(True, True, kw)
     barrier()
+    if prev_overlap is None:
+        os.environ.pop("COR_STEP_OVERLAP")
+    else:
+        os.environ["COR_STEP_OVERLAP"] = prev_overlap
     events, ops.TIMING["events"] = ops.TIMING["events"], None
     per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in events.items()}   # ms per step
     calls = {k: len(v) // args.steps for k, v in events.items()}

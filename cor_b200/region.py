@@ -84,6 +84,22 @@ def _target_rows(dev, B, M, offset):
     return t
 
 
+_side_streams = {}
+
+
+def _side_stream(dev):
+    """One extra stream per device for the branch of the step that does not depend on the pooled rows."""
+    st = _side_streams.get(dev.index)
+    if st is None:
+        st = torch.cuda.Stream(device=dev)
+        _side_streams[dev.index] = st
+    return st
+
+
+def _overlap_enabled():
+    return os.environ.get("COR_STEP_OVERLAP", "1") != "0"
+
+
 class _FusedStepFn(torch.autograd.Function):
     """The whole region path as ONE autograd node: every kernel of the forward is launched back to
     back on the current stream, the backward is written out by hand, and no tensor glue (slices,
@@ -104,6 +120,29 @@ class _FusedStepFn(torch.autograd.Function):
         comb_c = comb.reshape(B, -1).float().contiguous()
         f32 = dict(dtype=torch.float32, device=dev)
         need_emb = emb.requires_grad
+        # 5. segmentation loss against the GT mask, resample fused.  It depends on neither the resampled weights nor the
+        #    pooled rows, so it is issued FIRST, on a side stream (a parallel branch once the step is captured in a CUDA
+        #    graph): its instruction-bound tiles run underneath the HBM-bound mask resample.
+        gt = masks[:, 0]                       # [B,Hm,Wm] view; read in place through its sample stride
+        Hm, Wm = gt.shape[1:]
+        if not (gt.stride(2) == 1 and gt.stride(1) == Wm):
+            gt = gt.contiguous()
+        N = B
+        H, W = pred_c.shape[2:]
+        out8 = torch.empty(8, **f32)
+        per = torch.empty((N, 8), **f32)
+        need_pred = pred.requires_grad
+        t_save = torch.empty((N, H, W), **f32) if need_pred else None
+        w_save = torch.empty((N, H, W), **f32) if need_pred else None
+        seg_work = ops._work(lib.cor_seg_loss_work_bytes(N, H, W), dev)
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if _overlap_enabled() else None
+        if side is not None:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side if side is not None else cur):
+            call("cor_seg_loss_fwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(gt), L.dtype_code(gt), _f(ops._mask_scale(gt, None)), N, H, W,
+                 Hm, Wm, _ll(gt.stride(0)), _f(1.0), _f(1.0), _f(0.25), _f(-1.0), _f(1.0), ptr(out8), ptr(per), ptr(t_save), ptr(w_save),
+                 ptr(seg_work))
         # 1. masks -> bf16 weights (+ raw fp32 weights for the backward) + full-resolution stats
         Rp = (M + 1 + 15) // 16 * 16
         w16 = ops._umma_weight_buffer(dev, B, Rp, M, P)
@@ -135,22 +174,6 @@ class _FusedStepFn(torch.autograd.Function):
         aux = torch.empty(lib.cor_fgbg_aux_floats(B, Cc), **f32)
         call("cor_fgbg_loss_fwd", dev, ptr(fg), _ll(M * Cc), ptr(bg), _ll(Cc), ptr(comb_c), _ll(Cc), ptr(stats), _ll(4 * M), B, Cc,
              int(bg_mode), ptr(out4), ptr(aux))
-        # 5. segmentation loss against the GT mask, resample fused
-        gt = masks[:, 0]                       # [B,Hm,Wm] view; read in place through its sample stride
-        Hm, Wm = gt.shape[1:]
-        if not (gt.stride(2) == 1 and gt.stride(1) == Wm):
-            gt = gt.contiguous()
-        N = B
-        H, W = pred_c.shape[2:]
-        out8 = torch.empty(8, **f32)
-        per = torch.empty((N, 8), **f32)
-        need_pred = pred.requires_grad
-        t_save = torch.empty((N, H, W), **f32) if need_pred else None
-        w_save = torch.empty((N, H, W), **f32) if need_pred else None
-        work = ops._work(lib.cor_seg_loss_work_bytes(N, H, W), dev)
-        call("cor_seg_loss_fwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(gt), L.dtype_code(gt), _f(ops._mask_scale(gt, None)), N, H, W,
-             Hm, Wm, _ll(gt.stride(0)), _f(1.0), _f(1.0), _f(0.25), _f(-1.0), _f(1.0), ptr(out8), ptr(per), ptr(t_save), ptr(w_save),
-             ptr(work))
         # 6. InfoNCE of every composed query against all (gathered) regions
         q16 = comb_c.to(torch.bfloat16)
         n_local = B * M
@@ -187,6 +210,8 @@ class _FusedStepFn(torch.autograd.Function):
         tgt = torch.empty((B,), **f32)
         call("cor_infonce_fwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), r16.shape[0], B, Cc, _f(inv_tau), ptr(nce), ptr(tgt))
         loss = torch.empty(1, **f32)
+        if side is not None:
+            cur.wait_stream(side)            # join: the combine needs the segmentation loss
         call("cor_step_combine", dev, ptr(out8), ptr(out4), ptr(nce), _f(w_fg), _f(w_bg), _f(nce_weight), ptr(loss))
         ctx.save_for_backward(pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32,
                               fg16, q_all, lse_all, tgt_all)
@@ -213,18 +238,24 @@ class _FusedStepFn(torch.autograd.Function):
             return (None,) * 11
         g = g_loss.reshape(1).float().contiguous()
         g_pred = g_emb = g_comb = None
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if (_overlap_enabled() and need_pred) else None
+
         def seg_bwd():
             if not need_pred:
                 return None
             N, H, W = t_save.shape
             gp = torch.empty_like(pred_c)
-            call("cor_seg_loss_bwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _f(1.0), _f(1.0),
-                 ptr(g), ptr(gp), L.dtype_code(gp))
-            return gp.to(pred_dt)
+            if side is not None:
+                side.wait_stream(cur)
+            with torch.cuda.stream(side if side is not None else cur):
+                call("cor_seg_loss_bwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _f(1.0), _f(1.0),
+                     ptr(g), ptr(gp), L.dtype_code(gp))
+            return gp
 
         px = ctx.px
-        if px is None:
-            g_pred = seg_bwd()
+        if px is None or side is not None:
+            g_pred = seg_bwd()               # side stream: runs underneath the InfoNCE / pooling backward
         # InfoNCE backward first: it WRITES g_regions (this rank's rows) and g_queries ...
         Nr = r16.shape[0]
         g_regions = torch.empty((n_local, Cc), **f32)
@@ -245,7 +276,8 @@ class _FusedStepFn(torch.autograd.Function):
                  ptr(g_all), ptr(g_q), ptr(work))
             if px is not None:
                 px.signal(1)
-                g_pred = seg_bwd()           # independent work between the signal and the pull hides the rank skew
+                if side is None:
+                    g_pred = seg_bwd()       # independent work between the signal and the pull hides the rank skew
                 px.reduce(g_regions)         # fixed rank order: bit-identical from run to run
             else:
                 torch.distributed.reduce_scatter_tensor(g_regions, g_all, op=torch.distributed.ReduceOp.SUM)
@@ -273,6 +305,10 @@ class _FusedStepFn(torch.autograd.Function):
             name = "cor_pool_bwd_umma" if lib.cor_pool_bwd_umma_ok(B, Cc, P, M, int(gs_bg_full is not None)) else "cor_pool_bwd_feat"
             call(name, dev, ptr(gs_fg), ptr(gs_bg_full), ptr(w32), _ll(P), B, Cc, P, M, ops.W_CLAMP, ptr(g_emb_c), L._DTYPES[g_emb_c.dtype])
             g_emb = g_emb_c.to(emb_dt)
+        if side is not None:
+            cur.wait_stream(side)
+        if g_pred is not None:
+            g_pred = g_pred.to(pred_dt)
         return g_pred, g_emb, g_comb, None, None, None, None, None, None, None, None
 
 
