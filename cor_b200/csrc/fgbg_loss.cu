@@ -58,20 +58,35 @@ __global__ void __launch_bounds__(1024) fgbg_reduce_kernel(const float* __restri
   block_sum<5>(v, scratch);  // v[4] is still 0 here
   const double nfg = v[1], nbg = v[3];
   if (bg_mode == 0 && bg && nbg > 0) {
+    // column statistics of the reference's broadcast: 256 columns x 4 row-parts per pass, the parts combined in a fixed order
+    __shared__ float colpart[3][4][256];
     const float sq = sqrtf((float)nbg);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int cl = threadIdx.x & 255, part = threadIdx.x >> 8;
+    for (int c0 = 0; c0 < C; c0 += 256) {
+      const int c = c0 + cl;
       float A = 0.f, S1 = 0.f, ss = 0.f;
-      for (int i = 0; i < n; ++i) {
-        if (rowstat[(long long)i * 8 + 6] > 0.f) {
-          const float x = bg[i * bg_stride + c], q = comb[i * comb_stride + c];
-          A += x / fmaxf(sq * fabsf(x), kCosEps);
-          S1 += q;
-          ss = fmaf(q, q, ss);
+      if (c < C) {
+#pragma unroll 4
+        for (int i = part; i < n; i += 4) {
+          if (rowstat[(long long)i * 8 + 6] > 0.f) {
+            const float x = bg[i * bg_stride + c], q = comb[i * comb_stride + c];
+            A += x / fmaxf(sq * fabsf(x), kCosEps);
+            S1 += q;
+            ss = fmaf(q, q, ss);
+          }
         }
       }
-      const float s2 = fmaxf(sqrtf(ss), kCosEps);
-      colstat[c] = A; colstat[C + c] = S1; colstat[2 * C + c] = s2;
-      v[4] += (double)(A * S1 / s2);
+      __syncthreads();
+      colpart[0][part][cl] = A; colpart[1][part][cl] = S1; colpart[2][part][cl] = ss;
+      __syncthreads();
+      if (part == 0 && c < C) {
+        A = (colpart[0][0][cl] + colpart[0][1][cl]) + (colpart[0][2][cl] + colpart[0][3][cl]);
+        S1 = (colpart[1][0][cl] + colpart[1][1][cl]) + (colpart[1][2][cl] + colpart[1][3][cl]);
+        ss = (colpart[2][0][cl] + colpart[2][1][cl]) + (colpart[2][2][cl] + colpart[2][3][cl]);
+        const float s2 = fmaxf(sqrtf(ss), kCosEps);
+        colstat[c] = A; colstat[C + c] = S1; colstat[2 * C + c] = s2;
+        v[4] += (double)(A * S1 / s2);
+      }
     }
   }
   __syncthreads();

@@ -280,19 +280,22 @@ __global__ void __launch_bounds__(256, 5) mask_prep_staged_kernel(const T* __res
   }
 }
 
-// stats[n] = {sum m, sum (1-m), den, den_bf16}; fixed-order reduction of the chunk partials.
-__global__ void mask_prep_reduce_kernel(const double* __restrict__ part, int n_masks, int chunks, float mscale,
-                                        int one_minus_direct, float* __restrict__ stats) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// stats[n] = {sum m, sum (1-m), den, den_bf16}; fixed-order reduction of the chunk partials: one warp per mask, lane k
+// sums chunks k, k+32, ... in order, then a fixed shuffle tree (deterministic; the loads of a mask are all in flight at once).
+__global__ void __launch_bounds__(256) mask_prep_reduce_kernel(const double* __restrict__ part, int n_masks, int chunks, float mscale,
+                                                               int one_minus_direct, float* __restrict__ stats) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (n >= n_masks) return;
   double a = 0, b = 0, c = 0, d = 0;
-  for (int k = 0; k < chunks; ++k) {
-    const double* o = part + ((long long)n * chunks + k) * 4;
-    a += o[0]; b += o[1]; c += o[2]; d += o[3];
+  for (int k = lane; k < chunks; k += 32) {
+    const double2* o = reinterpret_cast<const double2*>(part + ((long long)n * chunks + k) * 4);
+    const double2 v0 = o[0], v1 = o[1];
+    a += v0.x; b += v0.y; c += v1.x; d += v1.y;
   }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+  if (lane != 0) return;
   float* s = stats + (long long)n * 4;
   const double sm = a * (double)mscale;
-  s[0] = (float)sm;
   // one_minus_direct 1: b is sum(1-m) accumulated directly (f32 masks);
   //                  0: b is the element count, sum(1-m) = count - sum (bf16 masks);
   //                  2: u8 masks, exact integers: (count*vmax - sum_bytes) * scale with vmax = round(1/scale)
@@ -300,6 +303,7 @@ __global__ void mask_prep_reduce_kernel(const double* __restrict__ part, int n_m
   if (one_minus_direct == 1) om = b;
   else if (one_minus_direct == 2) om = (b * (double)lrintf(1.0f / mscale) - a) * (double)mscale;
   else om = b - sm;
+  s[0] = (float)sm;
   s[1] = (float)fmax(om, 0.0);
   s[2] = (float)c;
   s[3] = (float)d;
@@ -394,6 +398,6 @@ extern "C" int cor_mask_prep(const void* masks, int mask_dtype, float mask_scale
   }
   int rc = check_launch("mask_prep_kernel");
   if (rc) return rc;
-  mask_prep_reduce_kernel<<<ceil_div(n_masks, 128), 128, 0, st>>>(part, n_masks, chunks, mask_scale, direct, stats);
+  mask_prep_reduce_kernel<<<ceil_div(n_masks, 8), 256, 0, st>>>(part, n_masks, chunks, mask_scale, direct, stats);
   return check_launch("mask_prep_reduce_kernel");
 }

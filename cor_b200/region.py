@@ -139,7 +139,13 @@ class _FusedStepFn(torch.autograd.Function):
         side = _side_stream(dev) if _overlap_enabled() else None
         if side is not None:
             side.wait_stream(cur)
+        q16 = torch.empty((B, comb_c.shape[1]), dtype=torch.bfloat16, device=dev)
+        ev_q = None
         with torch.cuda.stream(side if side is not None else cur):
+            q16.copy_(comb_c)                # bf16 queries for the similarity stage, off the main chain
+            if side is not None:
+                ev_q = torch.cuda.Event()
+                ev_q.record(side)
             call("cor_seg_loss_fwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(gt), L.dtype_code(gt), _f(ops._mask_scale(gt, None)), N, H, W,
                  Hm, Wm, _ll(gt.stride(0)), _f(1.0), _f(1.0), _f(0.25), _f(-1.0), _f(1.0), ptr(out8), ptr(per), ptr(t_save), ptr(w_save),
                  ptr(seg_work))
@@ -165,17 +171,22 @@ class _FusedStepFn(torch.autograd.Function):
              None, _f(0.0), ptr(fg), ptr(fg16), ptr(inv_fg))
         if px is not None:
             px.signal(0)                     # the bg rows, fg/bg loss and segmentation loss below hide the rank skew
+        # 4. background rows + fg / bg cosine losses on the GT rows (row b*M of fg, row b of bg): a second branch off the
+        #    fg rows, on the side stream, parallel to the similarity / InfoNCE chain below
         bg = torch.empty((B, Cc), **f32)
         inv_bg = torch.empty((B,), **f32)
-        call("cor_rows_finalize", dev, ptr(part), 1, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, 3:]), 4 * M, _f(1e-8), B, Cc, 1, 1,
-             ptr(part[0, :, M, :]), _f(float(P)), ptr(bg), None, ptr(inv_bg))
-        # 4. fg / bg cosine losses on the GT rows (row b*M of fg, row b of bg)
         out4 = torch.empty(4, **f32)
         aux = torch.empty(lib.cor_fgbg_aux_floats(B, Cc), **f32)
-        call("cor_fgbg_loss_fwd", dev, ptr(fg), _ll(M * Cc), ptr(bg), _ll(Cc), ptr(comb_c), _ll(Cc), ptr(stats), _ll(4 * M), B, Cc,
-             int(bg_mode), ptr(out4), ptr(aux))
+        if side is not None:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side if side is not None else cur):
+            call("cor_rows_finalize", dev, ptr(part), 1, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, 3:]), 4 * M, _f(1e-8), B, Cc, 1, 1,
+                 ptr(part[0, :, M, :]), _f(float(P)), ptr(bg), None, ptr(inv_bg))
+            call("cor_fgbg_loss_fwd", dev, ptr(fg), _ll(M * Cc), ptr(bg), _ll(Cc), ptr(comb_c), _ll(Cc), ptr(stats), _ll(4 * M), B, Cc,
+                 int(bg_mode), ptr(out4), ptr(aux))
         # 6. InfoNCE of every composed query against all (gathered) regions
-        q16 = comb_c.to(torch.bfloat16)
+        if ev_q is not None:
+            cur.wait_event(ev_q)
         n_local = B * M
         inv_tau = 1.0 / float(tau)
         # A/B on one 8xB200 box (profiles/README.md): reduce-scatter of the region gradient 0.951 ms/step, collective-free
