@@ -178,13 +178,26 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def _negatives_note():
+    """How the cross-rank negatives travel in THIS run (decided at the first multi-rank step)."""
+    try:
+        from cor_b200 import peer
+        if any(px.ok for px in peer._CACHE.values()):
+            return "regions of all ranks, gathered by our NVLink peer-memory kernels (csrc/peer.cu); gradient reduced the same way"
+    except Exception:
+        pass
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return "regions all-gathered across ranks (NCCL), gradient reduce-scattered (NCCL)"
+    return "all regions of the batch (single rank)"
+
+
 def workload_config(cfg, args, sample_triplets=None):
     c = {"workload": f"CORE fwd+bwd region path, batch {cfg['B']} triplets x {cfg['M']} masks per GPU, "
                      f"{cfg['H']}x{cfg['W']} {args.mask_dtype} masks, bf16 features [B,{cfg['C']},{cfg['h']},{cfg['w']}], "
                      f"logits [B,1,{cfg['hp']},{cfg['wp']}] (BASELINE.json configs[1])",
          "triplets_per_gpu": cfg["B"], "masks_per_triplet": cfg["M"], "feature_map": [cfg["C"], cfg["h"], cfg["w"]],
          "mask_size": [cfg["H"], cfg["W"]], "mask_dtype": args.mask_dtype, "tau": cfg["tau"], "backward": True,
-         "emb_grad": True, "negatives": "all-gathered across ranks (NCCL)",
+         "emb_grad": True, "negatives": _negatives_note(),
          "l2": "inputs (>= 1 GiB of masks per step) exceed the 126 MB L2; no explicit flush"}
     if sample_triplets is not None:
         c["cpu_sample_triplets"] = sample_triplets
