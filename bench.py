@@ -179,15 +179,10 @@ def run_reference(args, cfg):
 
 
 def _negatives_note():
-    """How the cross-rank negatives travel in THIS run (decided at the first multi-rank step)."""
-    try:
-        from cor_b200 import peer
-        if any(px.ok for px in peer._CACHE.values()):
-            return "regions of all ranks, gathered by our NVLink peer-memory kernels (csrc/peer.cu); gradient reduced the same way"
-    except Exception:
-        pass
+    """Where the InfoNCE negatives come from (same text on both arms of the bench)."""
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        return "regions all-gathered across ranks (NCCL), gradient reduce-scattered (NCCL)"
+        return ("regions of all ranks: gathered / gradient reduced by our NVLink peer-memory kernels (csrc/peer.cu) on one node, "
+                "NCCL all-gather / reduce-scatter with COR_PEER=0")
     return "all regions of the batch (single rank)"
 
 
