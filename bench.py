@@ -151,6 +151,36 @@ def cpu_baseline(inputs_cpu, cfg, triplets, iters, warm=1):
                       f"({med * 1e3:.0f} ms/step); oracle/aten_port.py = reference ATen op sequence"}, med
 
 
+def torch_eager_gpu_baseline(inp, cfg, iters=5, warm=2):
+    """the reference's op sequence (oracle/aten_port.py) run by PyTorch eager ON THE SAME B200, full batch,
+    fp32 and under bf16 autocast (how the reference trains, utils/trainer_v3_g.py:51) - the fair same-box bar next to the
+    CPU baseline.  Checker code used as a baseline only; nothing of it is on the product path."""
+    out = {}
+    sample = {k: (v.float() if v.is_floating_point() else v.float() / 255.0) for k, v in inp.items()}
+    for name, autocast in (("f32", False), ("bf16_autocast", True)):
+        try:
+            def one():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    return cpu_port_step(sample, cfg["tau"])
+            for _ in range(warm):
+                one()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(iters):
+                one()
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / iters
+            out[name] = {"value": cfg["B"] / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": iters}
+        except Exception as e:  # noqa: BLE001 - a baseline must never take the bench down
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    out["what"] = ("reference ATen op sequence (oracle/aten_port.py, multi-mask recipe of SURVEY 8c) under PyTorch eager on this GPU, "
+                   f"full batch of {cfg['B']} triplets x {cfg['M']} masks, fwd+bwd, device-resident inputs; includes float(loss)")
+    return out
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -430,6 +460,11 @@ def main():
         except Exception as e:   # the variant must never take the headline down with it
             variants["u8_masks"] = {"error": f"{type(e).__name__}: {e}"}
 
+    eager_gpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        trace("torch eager on the GPU")
+        eager_gpu = torch_eager_gpu_baseline(inp, cfg)
+
     trace("done")
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -442,6 +477,8 @@ def main():
                 "loss": float(loss.detach())}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager_gpu is not None:
+            line["torch_eager_gpu"] = eager_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         # NCCL communicators captured in a CUDA graph can stall destroy_process_group(): release the

@@ -132,6 +132,6 @@ def region_step_loss(pred, emb, comb, masks, tau: float = 0.07, nce_weight: floa
     regions = multi_mask_regions(emb, masks).reshape(B * M, -1)
     if regions_all is None:
         regions_all = regions
-    targets = torch.arange(B) * M + target_offset
+    targets = torch.arange(B, device=masks.device) * M + target_offset
     nce = infonce(regions_all, comb[:, 0, :].float(), targets, tau)
     return base + nce_weight * nce, regions
