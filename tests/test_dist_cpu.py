@@ -100,3 +100,17 @@ def test_single_process_is_identity():
     assert cdist.all_gather_rows(x) is x
     i, s = cdist.merge_topk(torch.arange(6).view(2, 3), torch.ones(2, 3), 10, 2)
     assert i.tolist() == [[10, 11], [13, 14]]
+
+
+def _peer_rank(rank, ws):
+    from cor_b200 import peer
+    # gloo group on CPU: the NVLink peer exchange must step aside (-> the torch.distributed collectives), never raise
+    return peer.get_exchange(64, 32, torch.device("cpu")) is None and peer.enabled()
+
+
+def test_peer_exchange_steps_aside_without_nccl(monkeypatch):
+    from cor_b200 import peer
+    assert peer.get_exchange(64, 32, torch.device("cpu")) is None          # not distributed at all
+    assert all(run_ranks(_peer_rank))
+    monkeypatch.setenv("COR_PEER", "0")
+    assert not peer.enabled()
