@@ -40,11 +40,13 @@ def _sig(lib, name, restype, *argtypes):
 
 
 def load(path: str = LIB_PATH):
-    """dlopen the library (works without a GPU: cudart is linked statically) and type every entry."""
+    """dlopen the library (works without a GPU: cudart is linked statically) and type every entry.
+    ``COR_B200_LIB`` points at another build of the same ABI (A/B runs of two kernel versions on one box)."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
+        path = os.environ.get("COR_B200_LIB", path)
         if not os.path.exists(path):
             raise CorError(
                 f"{path} not found: build it with `python -m cor_b200.build` (nvcc, sm_100a). "
