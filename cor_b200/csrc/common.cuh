@@ -15,6 +15,9 @@ int check_launch(const char* what);   // cudaGetLastError -> COR_ECUDA
 int sm_count();                       // cached multiprocessor count of the current device
 // lse[q] from `nparts` (max,sum) partials laid out [qtile][nparts][qt][2] (sim_stream.cu)
 int launch_lse_combine(const float* part, int Nq, int nparts, int qt, float* lse, cudaStream_t st);
+// tcgen05 similarity producer (sim_umma.cu); nparts/qt non-NULL: leave the LSE partials in `work`, report their layout
+int sim_umma_launch(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse, void* work,
+                    int* nparts, int* qt, cudaStream_t st);
 
 #define COR_REQUIRE(cond, ...)          \
   do {                                  \

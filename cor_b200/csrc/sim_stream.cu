@@ -152,6 +152,49 @@ __global__ void __launch_bounds__(1024) infonce_fwd_kernel(const bf16* __restric
   if (threadIdx.x == 0) loss[0] = (float)(acc[0] / (double)Nq);
 }
 
+// ---- the fused step's tail in ONE launch: merge of the log-sum-exp partials (as sim_lse_combine_kernel), target
+//      logits, mean InfoNCE loss and the step's total loss (as step_combine_kernel).  One CTA, one warp per query.
+__global__ void __launch_bounds__(1024) infonce_tail_kernel(const float* __restrict__ part, int nparts, int qt,
+                                                            const bf16* __restrict__ regions, const bf16* __restrict__ queries,
+                                                            const long long* __restrict__ targets, int Nr, int Nq, int D, float inv_tau,
+                                                            float* __restrict__ lse, float* __restrict__ nce, float* __restrict__ tgt_logit,
+                                                            const float* __restrict__ seg, const float* __restrict__ fgbg, float w_fg,
+                                                            float w_bg, float w_nce, float* __restrict__ total) {
+  __shared__ double scratch[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  double acc[1] = {0.0};
+  for (int q = warp; q < Nq; q += nwarp) {
+    const int tile = q / qt, ql = q % qt;
+    const float* base = part + ((long long)tile * nparts * qt + ql) * 2;
+    float M = -INFINITY;
+    for (int p = lane; p < nparts; p += 32) M = fmaxf(M, base[(long long)p * qt * 2]);
+    M = warp_max(M);
+    double a = 0.0;
+    for (int p = lane; p < nparts; p += 32) {
+      const float pm = base[(long long)p * qt * 2], ps = base[(long long)p * qt * 2 + 1];
+      if (pm != -INFINITY) a += (double)ps * exp((double)pm - (double)M);
+    }
+    a = warp_sum(a);
+    long long t = targets[q];
+    t = t < 0 ? 0 : (t >= Nr ? Nr - 1 : t);
+    float d = 0.f;
+    for (int k = lane; k < D; k += 32) d = fmaf(__bfloat162float(queries[(long long)q * D + k]), __bfloat162float(regions[t * D + k]), d);
+    d = warp_sum(d);
+    if (lane == 0) {
+      const float l = M + (float)log(a);
+      lse[q] = l;
+      tgt_logit[q] = d;
+      acc[0] += (double)l - (double)d * (double)inv_tau;
+    }
+  }
+  block_sum<1>(acc, scratch);
+  if (threadIdx.x == 0) {
+    const float v = (float)(acc[0] / (double)Nq);
+    nce[0] = v;
+    if (total) total[0] = seg[0] + w_fg * fgbg[0] + w_bg * fgbg[1] + w_nce * v;
+  }
+}
+
 // ---- InfoNCE backward (streaming; D <= 256) ------------------------------------------------------------
 //   coef[q,r] = (exp(S[q,r]/tau - lse[q]) - [r == t(q)]) * g / (tau * Nq)
 //   g_regions[r,:] = sum_q coef[q,r] Q[q,:]      g_queries[q,:] = sum_r coef[q,r] R[r,:]
@@ -536,22 +579,52 @@ extern "C" int cor_l2_normalize(const void* x, int x_dtype, int n, int D, float*
   return check_launch("l2_normalize_kernel");
 }
 
-extern "C" int cor_sim_stream_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S,
-                                  float* lse, void* work, cor_stream_t stream) {
-  COR_REQUIRE(regions && queries && (S || lse), "cor_sim_stream_fwd: null pointer");
-  COR_REQUIRE(Nr > 0 && Nq > 0 && D > 0 && D % 8 == 0, "cor_sim_stream_fwd: need D %% 8 == 0 (D=%d)", D);
-  COR_REQUIRE(!lse || work, "cor_sim_stream_fwd: lse needs a work buffer");
-  COR_REQUIRE((((uintptr_t)regions) & 15) == 0, "cor_sim_stream_fwd: regions must be 16-byte aligned");
+static int sim_stream_launch(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse,
+                             void* work, int* nparts, int* qt, cudaStream_t st) {
+  const bool want_lse = lse || nparts;
+  COR_REQUIRE(regions && queries && (S || want_lse), "cor_sim_stream: null pointer");
+  COR_REQUIRE(Nr > 0 && Nq > 0 && D > 0 && D % 8 == 0, "cor_sim_stream: need D %% 8 == 0 (D=%d)", D);
+  COR_REQUIRE(!want_lse || work, "cor_sim_stream: lse needs a work buffer");
+  COR_REQUIRE((((uintptr_t)regions) & 15) == 0, "cor_sim_stream: regions must be 16-byte aligned");
   const size_t smem = (size_t)kQT * D * sizeof(float);
-  COR_REQUIRE(smem <= 96 * 1024, "cor_sim_stream_fwd: D=%d too large", D);
-  cudaStream_t st = as_stream(stream);
+  COR_REQUIRE(smem <= 96 * 1024, "cor_sim_stream: D=%d too large", D);
   COR_CUDA(cudaFuncSetAttribute(sim_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ctas = stream_region_ctas(Nr), qtiles = ceil_div(Nq, kQT);
-  float* part = lse ? (float*)work : nullptr;
+  float* part = want_lse ? (float*)work : nullptr;
   sim_stream_kernel<<<dim3(ctas, qtiles), 256, smem, st>>>((const bf16*)regions, (const bf16*)queries, Nr, Nq, D, inv_tau, S, part);
   int rc = check_launch("sim_stream_kernel");
-  if (rc || !lse) return rc;
+  if (rc || !want_lse) return rc;
+  if (nparts) {                       // deferred: the caller merges the partials (cor_infonce_tail)
+    *nparts = ctas;
+    *qt = kQT;
+    return COR_OK;
+  }
   return launch_lse_combine(part, Nq, ctas, kQT, lse, st);
+}
+
+extern "C" int cor_sim_stream_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S,
+                                  float* lse, void* work, cor_stream_t stream) {
+  return sim_stream_launch(regions, queries, Nr, Nq, D, inv_tau, S, lse, work, nullptr, nullptr, as_stream(stream));
+}
+
+extern "C" int cor_sim_lse_parts(int engine, const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, void* work,
+                                 int* nparts, int* qt, cor_stream_t stream) {
+  COR_REQUIRE(nparts && qt, "cor_sim_lse_parts: null pointer");
+  if (engine == 1) return cor::sim_umma_launch(regions, queries, Nr, Nq, D, inv_tau, nullptr, nullptr, work, nparts, qt, as_stream(stream));
+  COR_REQUIRE(engine == 0, "cor_sim_lse_parts: engine %d (0 = stream, 1 = umma)", engine);
+  return sim_stream_launch(regions, queries, Nr, Nq, D, inv_tau, nullptr, nullptr, work, nparts, qt, as_stream(stream));
+}
+
+extern "C" int cor_infonce_tail(const float* lse_part, int nparts, int qt, const void* regions, const void* queries,
+                                const long long* targets, int Nr, int Nq, int D, float inv_tau, float* lse, float* nce, float* tgt_logit,
+                                const float* seg, const float* fgbg, float w_fg, float w_bg, float w_nce, float* total,
+                                cor_stream_t stream) {
+  COR_REQUIRE(lse_part && regions && queries && targets && lse && nce && tgt_logit, "cor_infonce_tail: null pointer");
+  COR_REQUIRE(nparts > 0 && qt > 0 && Nr > 0 && Nq > 0 && D > 0, "cor_infonce_tail: bad sizes");
+  COR_REQUIRE(!total || (seg && fgbg), "cor_infonce_tail: total needs seg and fgbg");
+  infonce_tail_kernel<<<1, 1024, 0, as_stream(stream)>>>(lse_part, nparts, qt, (const bf16*)regions, (const bf16*)queries, targets, Nr, Nq, D,
+                                                        inv_tau, lse, nce, tgt_logit, seg, fgbg, w_fg, w_bg, w_nce, total);
+  return check_launch("infonce_tail_kernel");
 }
 
 extern "C" int cor_infonce_fwd(const void* regions, const void* queries, const long long* targets, const float* lse, int Nr,

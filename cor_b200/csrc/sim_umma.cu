@@ -212,11 +212,13 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
 
 using namespace cor;
 
-extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse,
-                                void* work, cor_stream_t stream) {
-  COR_REQUIRE(regions && queries && (S || lse), "cor_sim_umma_fwd: null pointer");
+namespace cor {
+int sim_umma_launch(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse, void* work,
+                    int* nparts, int* qt, cudaStream_t st) {
+  const bool want_lse = lse || nparts;
+  COR_REQUIRE(regions && queries && (S || want_lse), "cor_sim_umma_fwd: null pointer");
   COR_REQUIRE(Nr > 0 && Nq > 0 && D % kSimBK == 0 && D >= kSimBK && D <= kSimMaxKB * kSimBK, "cor_sim_umma_fwd: need D in {64,128,192,256} (D=%d)", D);
-  COR_REQUIRE(!lse || work, "cor_sim_umma_fwd: lse needs a work buffer");
+  COR_REQUIRE(!want_lse || work, "cor_sim_umma_fwd: lse needs a work buffer");
   const int qtiles = ceil_div(Nq, kSimBM), ntiles = ceil_div(Nr, kSimBN);
   // CTAs that walk the same region tiles for different query tiles can form a cluster (along grid.y) and share every
   // region stage through TMA multicast (L2 -> SM traffic of the region stream / cluster size).  Measured on B200
@@ -239,9 +241,8 @@ extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr
   if (nstages > kSimMaxStages) nstages = kSimMaxStages;
   if (const char* e = getenv("COR_SIM_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= nstages) nstages = v; }   // A/B knob
   const size_t smem = (size_t)q_slots * kSimABytes + (size_t)nstages * kSimBBytes + sizeof(SimSmemTail) + 1024;
-  cudaStream_t st = as_stream(stream);
   COR_CUDA(cudaFuncSetAttribute(sim_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  float* part = lse ? (float*)work : nullptr;
+  float* part = want_lse ? (float*)work : nullptr;
   const int nkb_arg = nkb;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(gx, qtiles);
@@ -267,7 +268,18 @@ extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr
   }
   COR_CUDA(cudaLaunchKernelEx(&cfg, sim_umma_kernel, tmQ, tmR, Nr, Nq, nkb_arg, nstages, q_slots, cl, inv_tau, S, part));
   rc = check_launch("sim_umma_kernel");
-  if (rc || !lse) return rc;
+  if (rc || !want_lse) return rc;
+  if (nparts) {                       // deferred: the caller merges the partials (cor_infonce_tail)
+    *nparts = gx;
+    *qt = kSimBM;
+    return COR_OK;
+  }
   // inactive query rows of a half-empty last tile publish nothing; the combine only reads rows < Nq
   return launch_lse_combine(part, Nq, gx, kSimBM, lse, st);
+}
+}  // namespace cor
+
+extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse,
+                                void* work, cor_stream_t stream) {
+  return cor::sim_umma_launch(regions, queries, Nr, Nq, D, inv_tau, S, lse, work, nullptr, nullptr, as_stream(stream));
 }

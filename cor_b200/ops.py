@@ -29,7 +29,7 @@ _KERNELS_PER_CALL = {
     "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 1, "cor_rows_finalize": 1,
     "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_umma": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
     "cor_fgbg_loss_bwd": 1, "cor_step_combine": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
-    "cor_sim_umma_fwd": 2, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
+    "cor_sim_umma_fwd": 2, "cor_sim_lse_parts": 1, "cor_infonce_tail": 1, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
     "cor_val_post": 3, "cor_soft_metrics": 2,
 }
 
@@ -437,6 +437,20 @@ def _sim_forward(r16, q16, inv_tau, want_S, want_lse, engine):
     name = "cor_sim_umma_fwd" if _sim_engine(Nq, Nr, D, engine) == "umma" else "cor_sim_stream_fwd"
     _call(name, dev, ptr(r16), ptr(q16), Nr, Nq, D, _f(inv_tau), ptr(S), ptr(lse), ptr(work))
     return S, lse
+
+
+def _sim_lse_parts(r16, q16, inv_tau, engine):
+    """Similarity producer that leaves its log-sum-exp partials in a work buffer: (work, nparts, qt) for cor_infonce_tail."""
+    import ctypes as C
+    dev = r16.device
+    Nr, D = r16.shape
+    Nq = q16.shape[0]
+    lib = L.load()
+    work = _work(lib.cor_sim_work_bytes(Nq, Nr, D), dev)
+    nparts, qt = C.c_int(0), C.c_int(0)
+    eng = 1 if _sim_engine(Nq, Nr, D, engine) == "umma" else 0
+    _call("cor_sim_lse_parts", dev, eng, ptr(r16), ptr(q16), Nr, Nq, D, _f(inv_tau), ptr(work), C.byref(nparts), C.byref(qt))
+    return work, nparts.value, qt.value
 
 
 def _to_bf16_rows(x: torch.Tensor) -> torch.Tensor:

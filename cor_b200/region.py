@@ -211,19 +211,29 @@ class _FusedStepFn(torch.autograd.Function):
                 tgt_all = (ar // B) * n_local + (ar % B) * M - offset       # target rows local to THIS rank
             else:
                 q_all = lse_all = tgt_all = None
-                _, lse = ops._sim_forward(r16, q16, inv_tau, False, True, sim_engine)
+                lse = None
         else:
             r16, offset, ws = fg16, 0, 1
             q_all = lse_all = tgt_all = None
-            _, lse = ops._sim_forward(r16, q16, inv_tau, False, True, sim_engine)
+            lse = None
         targets = _target_rows(dev, B, M, offset)
         nce = torch.empty(1, **f32)
         tgt = torch.empty((B,), **f32)
-        call("cor_infonce_fwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), r16.shape[0], B, Cc, _f(inv_tau), ptr(nce), ptr(tgt))
         loss = torch.empty(1, **f32)
-        if side is not None:
-            cur.wait_stream(side)            # join: the combine needs the segmentation loss
-        call("cor_step_combine", dev, ptr(out8), ptr(out4), ptr(nce), _f(w_fg), _f(w_bg), _f(nce_weight), ptr(loss))
+        if lse is None:
+            # similarity with its log-sum-exp partials left in the work buffer, then ONE tail kernel: partial merge ->
+            # lse, target logits, InfoNCE mean and the step's total loss
+            sim_work, nparts, qt = ops._sim_lse_parts(r16, q16, inv_tau, sim_engine)
+            lse = torch.empty((B,), **f32)
+            if side is not None:
+                cur.wait_stream(side)        # join: the total needs the segmentation and fg/bg losses
+            call("cor_infonce_tail", dev, ptr(sim_work), nparts, qt, ptr(r16), ptr(q16), ptr(targets), r16.shape[0], B, Cc, _f(inv_tau),
+                 ptr(lse), ptr(nce), ptr(tgt), ptr(out8), ptr(out4), _f(w_fg), _f(w_bg), _f(nce_weight), ptr(loss))
+        else:
+            call("cor_infonce_fwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), r16.shape[0], B, Cc, _f(inv_tau), ptr(nce), ptr(tgt))
+            if side is not None:
+                cur.wait_stream(side)        # join: the combine needs the segmentation loss
+            call("cor_step_combine", dev, ptr(out8), ptr(out4), ptr(nce), _f(w_fg), _f(w_bg), _f(nce_weight), ptr(loss))
         ctx.save_for_backward(pred_c, t_save, w_save, per, fg, bg, inv_fg, inv_bg, comb_c, stats, out4, aux, r16, q16, targets, lse, w32,
                               fg16, q_all, lse_all, tgt_all)
         ctx.cfg = (B, M, Cc, h, w, float(inv_tau), float(nce_weight), int(bg_mode), float(w_fg), float(w_bg), ws, offset, n_local,
@@ -381,6 +391,7 @@ class StepBuffers:
         self.d = {"pred": mk((B, 1, hp, wp), emb_dtype), "emb": mk((B, C, h, w), emb_dtype), "comb": mk((B, 1, D), torch.float32),
                   "masks": mk((B, M, H, W), mask_dtype)}
         self.loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        self._seed = torch.ones((), dtype=torch.float32, device=self.device)
         self.graph = None
         self.loss = None
         self.grads = {}
@@ -401,7 +412,7 @@ class StepBuffers:
         emb = self.d["emb"].detach().requires_grad_(backward and emb_grad)
         out = region_step(pred, emb, comb, self.d["masks"], **kw)
         if backward:
-            out.loss.backward()
+            out.loss.backward(gradient=self._seed)      # a resident 1.0: no per-step fill kernel from autograd
         grads = {"pred": pred.grad, "comb": comb.grad, "emb": emb.grad}
         return out.loss.detach(), grads
 

@@ -174,6 +174,17 @@ int cor_sim_stream_fwd(const void* regions, const void* queries, int Nr, int Nq,
                        float* S, float* lse, void* work, cor_stream_t stream);
 int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau,
                      float* S, float* lse, void* work, cor_stream_t stream);
+/* As cor_sim_{stream,umma}_fwd asked for lse only, but the log-sum-exp partials stay in `work`, laid out
+ * [ceil(Nq / *qt)][*nparts][*qt][2] (running max, sum), for cor_infonce_tail to merge.  engine: 0 = stream, 1 = umma. */
+int cor_sim_lse_parts(int engine, const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau,
+                      void* work, int* nparts, int* qt, cor_stream_t stream);
+/* The tail of the fused step in ONE launch: merge of those partials -> lse [Nq]; tgt_logit and nce as cor_infonce_fwd;
+ * and, when total != NULL, total = seg[0] + w_fg * fgbg[0] + w_bg * fgbg[1] + w_nce * nce (= cor_step_combine,
+ * utils/trainer_v3_g.py:67-73 plus the Class-N term). */
+int cor_infonce_tail(const float* lse_part, int nparts, int qt, const void* regions, const void* queries,
+                     const long long* targets, int Nr, int Nq, int D, float inv_tau, float* lse, float* nce,
+                     float* tgt_logit, const float* seg, const float* fgbg, float w_fg, float w_bg, float w_nce,
+                     float* total, cor_stream_t stream);
 /* loss = mean_q (lse[q] - S[q, target[q]] / tau); tgt_logit [Nq] is S[q,target[q]] (f32). */
 int cor_infonce_fwd(const void* regions, const void* queries, const long long* targets, const float* lse,
                     int Nr, int Nq, int D, float inv_tau, float* loss, float* tgt_logit, cor_stream_t stream);

@@ -171,10 +171,12 @@ def test_pool_bwd_umma_vs_cuda_core(cfg):
     assert err < 6e-3, err
 
 
+@pytest.mark.parametrize("sim_engine", ["stream", "umma"])
 @pytest.mark.parametrize("bg_mode", [0, 1])
-def test_fused_step_equals_modular_ops(bg_mode):
-    """region_step's single-node fused path (hand-written backward) against the composition of the
-    modular autograd ops on the same inputs: loss parts and all three gradients."""
+def test_fused_step_equals_modular_ops(bg_mode, sim_engine):
+    """region_step's single-node fused path (hand-written backward, log-sum-exp partials of either similarity
+    producer merged by the one-launch tail kernel) against the composition of the modular autograd ops on the same
+    inputs: loss parts and all three gradients."""
     from cor_b200 import region, synth
     d = synth.make_triplets(73, B=3, M=20, C=128, h=16, w=16, H=64, W=64, hp=32, wp=32, degenerate=False)
     d["masks"][1, 0] = 0.0                      # an invalid GT mask
@@ -183,7 +185,7 @@ def test_fused_step_equals_modular_ops(bg_mode):
         p = cu(d["pred"], grad=True)
         c = cu(d["comb"], grad=True)
         e = torch.from_numpy(d["emb"]).bfloat16().to(dev()).requires_grad_(True)
-        o = region.region_step(p, e, c, cu(d["masks"]), tau=0.07, gather=False, bg_mode=bg_mode, fused=fused)
+        o = region.region_step(p, e, c, cu(d["masks"]), tau=0.07, gather=False, bg_mode=bg_mode, fused=fused, sim_engine=sim_engine)
         o.loss.backward()
         outs.append((o, p.grad.float(), c.grad.float(), e.grad.float()))
     (a, pa, ca, ea), (b, pb, cb, eb) = outs
