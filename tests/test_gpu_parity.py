@@ -394,7 +394,8 @@ def test_ragged_and_odd_shapes():
     from cor_b200 import ops, synth
     from oracle import np_oracle as no
     rng = np.random.default_rng(7)
-    for (B, M, C, h, w, H, W) in [(2, 3, 17, 9, 13, 37, 51), (1, 5, 40, 27, 27, 384, 384), (3, 1, 8, 5, 7, 5, 7), (1, 2, 130, 6, 6, 100, 90)]:
+    for (B, M, C, h, w, H, W) in [(2, 3, 17, 9, 13, 37, 51), (1, 5, 40, 27, 27, 384, 384), (3, 1, 8, 5, 7, 5, 7), (1, 2, 130, 6, 6, 100, 90),
+                                  (1, 2, 8, 9, 9, 6, 6), (2, 2, 16, 1, 1, 17, 5)]:          # up-sampled masks; a single feature pixel
         emb = rng.standard_normal((B, C, h, w)).astype(np.float32)
         masks = synth.make_masks(rng, B, M, H, W, soft=True, degenerate=False)
         p = ops.region_pool(cu(emb), cu(masks), transform=ops.W_CLAMP, normalize=True, pair=True, engine="stream")
@@ -402,7 +403,7 @@ def test_ragged_and_odd_shapes():
         close(p.bg, no.multi_mask_pool(emb, masks, background=True), rtol=2e-4, atol=2e-5)
         st = p.stats.cpu().numpy()
         np.testing.assert_allclose(st[:, 0], masks.reshape(B * M, -1).astype(np.float64).sum(1), rtol=1e-5)
-    for (N, H, W, Hm, Wm) in [(2, 33, 47, 70, 131), (1, 65, 64, 65, 64), (3, 7, 200, 28, 800)]:
+    for (N, H, W, Hm, Wm) in [(2, 33, 47, 70, 131), (1, 65, 64, 65, 64), (3, 7, 200, 28, 800), (2, 40, 8, 13, 5)]:   # last: mask coarser than the logits
         pred = rng.standard_normal((N, 1, H, W)).astype(np.float32)
         mask = synth.make_masks(rng, N, 1, Hm, Wm, soft=True, degenerate=False)
         close(ops.seg_loss(cu(pred), cu(mask)), no.segmentation_loss(pred, mask), rtol=1e-4, atol=1e-6)
