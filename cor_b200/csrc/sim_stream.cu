@@ -169,10 +169,12 @@ __global__ void __launch_bounds__(1024) infonce_tail_kernel(const float* __restr
     float M = -INFINITY;
     for (int p = lane; p < nparts; p += 32) M = fmaxf(M, base[(long long)p * qt * 2]);
     M = warp_max(M);
+    // fp32 rescale (expf of a non-positive argument, relative error ~1e-7) and fp64 only for the sum: the fp64 exp
+    // of sim_lse_combine_kernel costs microseconds on this single-CTA critical path
     double a = 0.0;
     for (int p = lane; p < nparts; p += 32) {
       const float pm = base[(long long)p * qt * 2], ps = base[(long long)p * qt * 2 + 1];
-      if (pm != -INFINITY) a += (double)ps * exp((double)pm - (double)M);
+      if (pm != -INFINITY) a += (double)(ps * expf(pm - M));
     }
     a = warp_sum(a);
     long long t = targets[q];
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(1024) infonce_tail_kernel(const float* __restr
     for (int k = lane; k < D; k += 32) d = fmaf(__bfloat162float(queries[(long long)q * D + k]), __bfloat162float(regions[t * D + k]), d);
     d = warp_sum(d);
     if (lane == 0) {
-      const float l = M + (float)log(a);
+      const float l = M + logf((float)a);
       lse[q] = l;
       tgt_logit[q] = d;
       acc[0] += (double)l - (double)d * (double)inv_tau;
