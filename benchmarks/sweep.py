@@ -121,6 +121,24 @@ def main():
             t = timeit(lambda: ops.topk_retrieve(R, Q, k), a.iters)
             emit(f"topk_retrieve (sim+select+rerank) Nq256 Nr4096 k{k}", t)
 
+    # ---- InfoNCE forward + backward: dense (tensor-core S + bf16 coefficients + library GEMMs) vs streaming backward
+    if want("nce"):
+        for (Nq, Nr, D) in [(256, 4096, 256), (1024, 102400, 256)]:
+            R = unit(Nr, D, g).requires_grad_(True)
+            Q = unit(Nq, D, g).requires_grad_(True)
+            tg = (torch.arange(Nq, device="cuda") * 7) % Nr
+            for eng in ("auto", "stream"):
+                if eng == "stream" and Nq * Nr > (1 << 24):
+                    iters = 3                      # the streaming backward takes milliseconds here
+                else:
+                    iters = a.iters
+
+                def fn():
+                    R.grad = Q.grad = None
+                    ops.infonce_loss(R, Q, tg, tau=0.07, engine=eng).backward()
+                t = timeit(fn, iters)
+                emit(f"infonce fwd+bwd ({'dense' if eng == 'auto' else 'streaming'} backward) Nq{Nq} Nr{Nr} D{D}", t, flops=6.0 * Nq * Nr * D)
+
     # ---- segmentation loss, validation post-process
     if want("seg"):
         for B in (16, 128):

@@ -23,6 +23,28 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// The driver call below needs a CUDA context current on the calling thread.  A thread that has only ever been handed
+// tensors (a fresh Python thread, autograd's backward thread when our node runs first) may have none yet, and the
+// runtime binds one lazily only on ITS OWN calls: bind the primary context of the device that owns `ptr`.
+static void bind_context_of(const void* ptr) {
+  typedef CUresult (*PtrAttrFn)(void*, CUpointer_attribute, CUdeviceptr);
+  static PtrAttrFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PtrAttrFn>(p);
+  }
+  int ordinal = -1;
+  if (!fn || fn(&ordinal, CU_POINTER_ATTRIBUTE_DEVICE_ORDINAL, (CUdeviceptr)(uintptr_t)ptr) != CUDA_SUCCESS || ordinal < 0) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) == cudaSuccess && a.type == cudaMemoryTypeDevice) ordinal = a.device;
+    else if (cudaGetDevice(&ordinal) != cudaSuccess) ordinal = 0;
+    cudaGetLastError();
+  }
+  cudaSetDevice(ordinal);
+}
+
 int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return COR_ECUDA;
@@ -34,9 +56,14 @@ int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
   cuuint64_t strides[1] = {cols * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT && r != CUDA_ERROR_NOT_INITIALIZED) break;
+    bind_context_of(base);            // no context on this thread yet: bind the owner's and try once more
+  }
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)", (int)r, (unsigned long long)rows,
               (unsigned long long)cols, box_rows, box_cols);

@@ -29,7 +29,7 @@ _KERNELS_PER_CALL = {
     "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 1, "cor_rows_finalize": 1,
     "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_umma": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
     "cor_fgbg_loss_bwd": 1, "cor_step_combine": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
-    "cor_sim_umma_fwd": 2, "cor_sim_lse_parts": 1, "cor_infonce_tail": 1, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
+    "cor_sim_umma_fwd": 2, "cor_infonce_coef": 1, "cor_sim_lse_parts": 1, "cor_infonce_tail": 1, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
     "cor_val_post": 3, "cor_soft_metrics": 2,
 }
 
@@ -464,6 +464,14 @@ def similarity(regions: torch.Tensor, queries: torch.Tensor, engine: str = "auto
     return S
 
 
+def _infonce_bwd_dense(Nq: int, Nr: int, D: int, engine: str) -> bool:
+    """Dense (GEMM) InfoNCE backward for the many-query regime; the streaming kernel keeps the few-query one (a rank's
+    own queries against gathered regions) and everything the tensor-core similarity kernel does not take."""
+    if engine == "stream":
+        return False
+    return Nq >= 128 and D in (64, 128, 192, 256) and Nq * Nr >= (1 << 19)
+
+
 class _InfoNCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, regions, queries, targets, tau, engine, regions_bf16):
@@ -479,6 +487,7 @@ class _InfoNCEFn(torch.autograd.Function):
         tgt = torch.empty((Nq,), dtype=torch.float32, device=dev)
         _call("cor_infonce_fwd", dev, ptr(r16), ptr(q16), ptr(tg), ptr(lse), Nr, Nq, D, _f(inv_tau), ptr(loss), ptr(tgt))
         ctx.save_for_backward(r16, q16, tg, lse)
+        ctx.engine = engine
         ctx.cfg = (inv_tau, regions.dtype, queries.dtype, tuple(regions.shape), tuple(queries.shape),
                    regions.requires_grad, queries.requires_grad)
         return loss[0].clone()
@@ -491,11 +500,21 @@ class _InfoNCEFn(torch.autograd.Function):
         Nr, D = r16.shape
         Nq = q16.shape[0]
         lib = L.load()
-        gr = torch.empty((Nr, D), dtype=torch.float32, device=dev)
-        gq = torch.empty((Nq, D), dtype=torch.float32, device=dev)
-        work = _work(lib.cor_sim_work_bytes(Nq, Nr, D), dev)
         gl = g.reshape(1).float().contiguous()
-        _call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(tg), ptr(lse), Nr, Nq, D, _f(inv_tau), ptr(gl), _f(1.0), ptr(gr), ptr(gq), ptr(work))
+        if _infonce_bwd_dense(Nq, Nr, D, ctx.engine):
+            # hundreds of queries: S on the tensor cores (our GEMM), the bf16 coefficient matrix in one pass, then two plain
+            # library GEMMs with fp32 output (dQ = P R, dR = P^T Q)
+            S, _ = _sim_forward(r16, q16, 1.0, True, False, "umma")
+            P = torch.empty((Nq, Nr), dtype=torch.bfloat16, device=dev)
+            _call("cor_infonce_coef", dev, ptr(S), ptr(lse), ptr(tg), Nq, Nr, _f(inv_tau), ptr(gl), _f(1.0), ptr(P))
+            del S
+            gq = torch.mm(P, r16, out_dtype=torch.float32) if q_need else None
+            gr = torch.mm(P.t(), q16, out_dtype=torch.float32) if r_need else None
+        else:
+            gr = torch.empty((Nr, D), dtype=torch.float32, device=dev)
+            gq = torch.empty((Nq, D), dtype=torch.float32, device=dev)
+            work = _work(lib.cor_sim_work_bytes(Nq, Nr, D), dev)
+            _call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(tg), ptr(lse), Nr, Nq, D, _f(inv_tau), ptr(gl), _f(1.0), ptr(gr), ptr(gq), ptr(work))
         return (gr.view(rshape).to(rdt) if r_need else None), (gq.view(qshape).to(qdt) if q_need else None), None, None, None, None
 
 

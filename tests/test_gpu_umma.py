@@ -236,3 +236,60 @@ def test_full_size_config2_tensor_core_step_vs_exact_engines():
     ia, _ = region.topk_regions(a.regions.reshape(B * M, 256), comb.reshape(B, 256), 5)
     ib, _ = region.topk_regions(a.regions.reshape(B * M, 256), comb.reshape(B, 256), 5, engine="stream")
     assert torch.equal(ia, ib)
+
+
+@pytest.mark.parametrize("shape", [(4096, 256, 256), (5001, 130, 128)])
+def test_infonce_dense_backward_vs_streaming_and_oracle(shape):
+    """Many-query InfoNCE backward (tensor-core S, bf16 coefficient matrix, two library GEMMs) against the exact
+    streaming backward and the ATen port.  bf16 coefficients: gradients agree to a few 1e-3 of their norm."""
+    from cor_b200 import ops, synth
+    from oracle import aten_port as ap
+    Nr, Nq, D = shape
+    assert ops._infonce_bwd_dense(Nq, Nr, D, "auto")
+    g = synth.make_gallery(31, Nr, Nq, D=D)
+    t = (np.arange(Nq) * 11) % Nr
+    grads = {}
+    for eng in ("auto", "stream"):
+        r, q = cu(g["regions"], grad=True), cu(g["queries"], grad=True)
+        loss = ops.infonce_loss(r, q, cu(t), tau=0.07, engine=eng)
+        (3.0 * loss).backward()
+        grads[eng] = (float(loss), r.grad.float(), q.grad.float())
+    rc, qc = torch.from_numpy(g["regions"]).requires_grad_(True), torch.from_numpy(g["queries"]).requires_grad_(True)
+    lc = ap.infonce(rc, qc, torch.from_numpy(t), 0.07)
+    (3.0 * lc).backward()
+    assert abs(grads["auto"][0] - float(lc)) < 1e-3 * abs(float(lc))
+    for i, ref in ((1, rc.grad), (2, qc.grad)):
+        a, s_ = grads["auto"][i].cpu(), grads["stream"][i].cpu()
+        assert float((a - s_).norm() / s_.norm()) < 4e-3
+        assert float((a - ref).norm() / ref.norm()) < 4e-3
+        assert float((a - ref).abs().max() / ref.abs().max()) < 1e-2
+
+
+def test_tensor_core_paths_from_a_thread_without_a_cuda_context():
+    """TMA descriptors are encoded through the driver API, which needs a context current on the CALLING thread; a fresh
+    Python thread (or autograd's backward thread when our node is the first to run) has none.  The library binds the
+    context of the device that owns the operand."""
+    import threading
+    from cor_b200 import ops, synth
+    g = synth.make_gallery(5, 512, 160, D=128)
+    r, q = cu(g["regions"]), cu(g["queries"])
+    want = ops.similarity(r, q, engine="stream").cpu()
+    torch.cuda.synchronize()
+    box = {}
+
+    def work():
+        try:
+            box["S"] = ops.similarity(r, q, engine="umma").cpu()
+        except Exception as e:  # noqa: BLE001
+            box["err"] = e
+
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    assert "err" not in box, box.get("err")
+    torch.testing.assert_close(box["S"], want, rtol=1e-3, atol=1e-3)
+    # autograd thread, our backward as the first node, dense (tensor-core) path
+    g2 = synth.make_gallery(6, 4096, 256, D=256)
+    r2, q2 = cu(g2["regions"], grad=True), cu(g2["queries"], grad=True)
+    ops.infonce_loss(r2, q2, cu((np.arange(256) * 3) % 4096), tau=0.07).backward()
+    assert torch.isfinite(r2.grad).all() and torch.isfinite(q2.grad).all()
