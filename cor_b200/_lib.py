@@ -79,6 +79,7 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_sim_stream_fwd", i, p, p, i, i, i, f, p, p, p, p)
         _sig(lib, "cor_sim_umma_fwd", i, p, p, i, i, i, f, p, p, p, p)
         _sig(lib, "cor_infonce_fwd", i, p, p, p, p, i, i, i, f, p, p, p)
+        _sig(lib, "cor_sim_umma_coef", i, p, p, i, i, i, f, p, p, p, f, p, p)
         _sig(lib, "cor_infonce_coef", i, p, p, p, i, i, f, p, f, p, p)
         _sig(lib, "cor_sim_lse_parts", i, i, p, p, i, i, i, f, p, C.POINTER(i), C.POINTER(i), p)
         _sig(lib, "cor_infonce_tail", i, p, i, i, p, p, p, i, i, i, f, p, p, p, p, p, f, f, f, p, p)

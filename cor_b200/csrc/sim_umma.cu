@@ -41,10 +41,21 @@ struct SimSmemTail {
   uint32_t tmem_base;
 };
 
+// Third epilogue mode (InfoNCE backward, many queries): the S tile leaves TMEM as the bf16 coefficient matrix
+//   P[q,r] = (exp(S[q,r]/tau - lse[q]) - [r == target(q)]) * g_loss[0] * g_mul / (tau * Nq)
+// so neither S nor an fp32 P is ever written; dQ = P R and dR = P^T Q follow as plain GEMMs.
+struct SimCoef {
+  const float* lse;
+  const long long* targets;
+  const float* g_loss;
+  float g_mul;
+  bf16* P;
+};
+
 // part layout (shared with the streaming producer's combine kernel): [qtile][gridDim.x][kSimBM][2]
 __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmR,
                                                           int Nr, int Nq, int nkb, int nstages, int q_slots, int cl, float inv_tau,
-                                                          float* __restrict__ S, float* __restrict__ part) {
+                                                          float* __restrict__ S, float* __restrict__ part, SimCoef coef) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   uint8_t* q_smem = base;                                                   // [half][kb] x 16 KB
@@ -131,6 +142,15 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
     const float c2 = inv_tau * 1.4426950408889634f;   // exp(x/tau) = exp2(x * c2)
     float m = -INFINITY, ssum = 0.f;               // running max of raw S and sum exp2((S - m) c2)
     const bool vec_ok = (Nr % 4 == 0) && ((((uintptr_t)S) & 15) == 0);
+    const bool want_coef = coef.P != nullptr;
+    const bool pvec_ok = (Nr % 8 == 0) && ((((uintptr_t)coef.P) & 15) == 0);
+    float neg_lse2 = 0.f, gscale = 0.f;
+    long long tq = -1;
+    if (want_coef && qok) {
+      neg_lse2 = -coef.lse[q] * 1.4426950408889634f;
+      gscale = coef.g_loss[0] * coef.g_mul * inv_tau / (float)Nq;
+      tq = coef.targets[q];
+    }
     int i = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
@@ -156,6 +176,31 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (j < nval) dst[j] = __uint_as_float(v[j]);
+            }
+          }
+          if (want_coef && qok) {
+            bf16* dst = coef.P + (long long)q * Nr + r0 + col;
+            const long long hit = tq - (long long)(r0 + col);        // position of the target inside this chunk, if any
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float c0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c2, neg_lse2));
+              float c1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c2, neg_lse2));
+              if (hit == 2 * j) c0 -= 1.f;
+              if (hit == 2 * j + 1) c1 -= 1.f;
+              __nv_bfloat162 pk = __floats2bfloat162_rn(c0 * gscale, c1 * gscale);
+              w[j] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+            if (pvec_ok && nval == 32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nval) {
+                  const uint32_t u = w[j >> 1];
+                  reinterpret_cast<uint16_t*>(dst)[j] = (uint16_t)((j & 1) ? (u >> 16) : (u & 0xffffu));
+                }
             }
           }
           if (part) {
@@ -213,10 +258,10 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
 using namespace cor;
 
 namespace cor {
-int sim_umma_launch(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse, void* work,
-                    int* nparts, int* qt, cudaStream_t st) {
+static int sim_umma_launch_impl(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse,
+                                void* work, int* nparts, int* qt, SimCoef coef, cudaStream_t st) {
   const bool want_lse = lse || nparts;
-  COR_REQUIRE(regions && queries && (S || want_lse), "cor_sim_umma_fwd: null pointer");
+  COR_REQUIRE(regions && queries && (S || want_lse || coef.P), "cor_sim_umma_fwd: null pointer");
   COR_REQUIRE(Nr > 0 && Nq > 0 && D % kSimBK == 0 && D >= kSimBK && D <= kSimMaxKB * kSimBK, "cor_sim_umma_fwd: need D in {64,128,192,256} (D=%d)", D);
   COR_REQUIRE(!want_lse || work, "cor_sim_umma_fwd: lse needs a work buffer");
   const int qtiles = ceil_div(Nq, kSimBM), ntiles = ceil_div(Nr, kSimBN);
@@ -266,7 +311,7 @@ int sim_umma_launch(const void* regions, const void* queries, int Nr, int Nq, in
       cfg.gridDim = dim3(gx, qtiles);
     }
   }
-  COR_CUDA(cudaLaunchKernelEx(&cfg, sim_umma_kernel, tmQ, tmR, Nr, Nq, nkb_arg, nstages, q_slots, cl, inv_tau, S, part));
+  COR_CUDA(cudaLaunchKernelEx(&cfg, sim_umma_kernel, tmQ, tmR, Nr, Nq, nkb_arg, nstages, q_slots, cl, inv_tau, S, part, coef));
   rc = check_launch("sim_umma_kernel");
   if (rc || !want_lse) return rc;
   if (nparts) {                       // deferred: the caller merges the partials (cor_infonce_tail)
@@ -277,7 +322,19 @@ int sim_umma_launch(const void* regions, const void* queries, int Nr, int Nq, in
   // inactive query rows of a half-empty last tile publish nothing; the combine only reads rows < Nq
   return launch_lse_combine(part, Nq, gx, kSimBM, lse, st);
 }
+
+int sim_umma_launch(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse, void* work,
+                    int* nparts, int* qt, cudaStream_t st) {
+  return sim_umma_launch_impl(regions, queries, Nr, Nq, D, inv_tau, S, lse, work, nparts, qt, SimCoef{nullptr, nullptr, nullptr, 0.f, nullptr}, st);
+}
 }  // namespace cor
+
+extern "C" int cor_sim_umma_coef(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, const float* lse,
+                                 const long long* targets, const float* g_loss, float g_mul, void* P_bf16, cor_stream_t stream) {
+  COR_REQUIRE(lse && targets && g_loss && P_bf16, "cor_sim_umma_coef: null pointer");
+  return cor::sim_umma_launch_impl(regions, queries, Nr, Nq, D, inv_tau, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   cor::SimCoef{lse, targets, g_loss, g_mul, (cor::bf16*)P_bf16}, cor::as_stream(stream));
+}
 
 extern "C" int cor_sim_umma_fwd(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse,
                                 void* work, cor_stream_t stream) {

@@ -185,6 +185,10 @@ int cor_infonce_tail(const float* lse_part, int nparts, int qt, const void* regi
                      const long long* targets, int Nr, int Nq, int D, float inv_tau, float* lse, float* nce,
                      float* tgt_logit, const float* seg, const float* fgbg, float w_fg, float w_bg, float w_nce,
                      float* total, cor_stream_t stream);
+/* The same coefficient matrix straight out of the tensor-core similarity kernel's epilogue (S is never written):
+ * regions / queries as cor_sim_umma_fwd, lse [Nq] from the forward. */
+int cor_sim_umma_coef(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, const float* lse,
+                      const long long* targets, const float* g_loss, float g_mul, void* P_bf16, cor_stream_t stream);
 /* Many-query backward: P [Nq, Nr] bf16 = (exp(S/tau - lse) - onehot(target)) * g_loss[0] * g_mul / (tau * Nq) from the
  * raw similarity matrix S [Nq, Nr] f32; the caller finishes with two plain GEMMs, dQ = P R and dR = P^T Q. */
 int cor_infonce_coef(const float* S, const float* lse, const long long* targets, int Nq, int Nr, float inv_tau,
