@@ -205,7 +205,7 @@ def run_reference(args, cfg):
                              "sample": f"each step = {triplets} triplets x {cfg['M']} masks (bounded sample of the {cfg['B']}-triplet batch), "
                                        "reference ATen op sequence (oracle/aten_port.py; the reference is Python and cannot travel)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_result(line)
 
 
 def _negatives_note():
@@ -258,7 +258,31 @@ def bind_to_gpu_numa(local):
         return None
 
 
+_RESULT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG=VERSION comes from the environment or from /etc/nccl.conf), so file descriptor 1 is pointed at stderr for
+    the whole run and the result line goes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_result(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
     ap_.add_argument("--steps", type=int, default=20)
@@ -291,8 +315,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's banner off stdout (env beats /etc/nccl.conf)
         dist.init_process_group("nccl", device_id=dev)
     trace("init done")
     hbm_peak, tc_peak, peak_kind = peaks()
@@ -394,9 +418,9 @@ def main():
     if args.no_e2e:
         clk.__exit__()
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": ms_step, "e2e": None,
+            emit_result({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "ms_per_step": ms_step, "e2e": None,
                               "roofline": roofline, "kernel_ms_per_step": per_kernel, "gpu_launches": launches, "graphed": graphed,
-                              "note": "profiling run"}), flush=True)
+                              "note": "profiling run"})
         if world > 1:
             bufs.graph = None
             barrier()
@@ -479,7 +503,7 @@ def main():
             line["cpu_baseline"] = cpu
         if eager_gpu is not None:
             line["torch_eager_gpu"] = eager_gpu
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if world > 1:
         # NCCL communicators captured in a CUDA graph can stall destroy_process_group(): release the
         # graph first, drain, and leave without the collective teardown.
