@@ -31,7 +31,7 @@ UNIT = "triplets/s"
 CFG = dict(B=16, M=64, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, tau=0.07)
 # dram__bytes_read.sum + dram__bytes_write.sum per mask_prep_kernel launch from the committed ncu --set full capture
 # (profiles/): filled in from the capture of the SAME configuration, else null.
-TRAFFIC_NCU = {"f32": 4303368320, "u8": None}   # profiles/r01_step_kernels_ncu_full_summary.csv: 4.294992 GB read + 8.376 MB written
+TRAFFIC_NCU = {"f32": 4304488392, "u8": None}   # profiles/r01_step_kernels_ncu_full_summary.csv: 4.295021 GB read + 9.467 MB written
 
 
 _T0 = time.perf_counter()
