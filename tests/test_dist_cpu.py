@@ -114,3 +114,42 @@ def test_peer_exchange_steps_aside_without_nccl(monkeypatch):
     assert all(run_ranks(_peer_rank))
     monkeypatch.setenv("COR_PEER", "0")
     assert not peer.enabled()
+
+
+def test_peer_exchange_wait_policy(monkeypatch):
+    """Host-side half of the peer protocol (cor_b200/peer.py): a wait_exit kernel is issued before a producer only when
+    no exchange on the OTHER channel ran since the last one on this channel (or, while capturing a CUDA graph, whenever
+    that cannot be proven from the recorded sequence).  Every exchange needs exactly one signal before it."""
+    from cor_b200 import peer
+    px = object.__new__(peer.PeerExchange)
+    px._last = None
+    calls = []
+    px._ctl = lambda name, ch: calls.append((name, ch))
+    capturing = {"v": False}
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: capturing["v"])
+
+    def exchange(ch):                      # what gather()/reduce() record
+        px._last = ch
+
+    # training loop: gather, reduce, gather, reduce -> never a wait
+    for _ in range(3):
+        px.before_produce(0); px.signal(0); exchange(0)
+        px.before_produce(1); px.signal(1); exchange(1)
+    assert [c for c in calls if c[0] == "cor_peer_wait_exit"] == []
+    assert [c for c in calls if c[0] == "cor_peer_signal"] == [("cor_peer_signal", 0), ("cor_peer_signal", 1)] * 3
+    # forward-only loop: the same channel twice in a row -> wait before the second producer
+    calls.clear()
+    px._last = None
+    px.before_produce(0); exchange(0)
+    px.before_produce(0); exchange(0)
+    assert calls == [("cor_peer_wait_exit", 0)]
+    # capture: first producer of the graph with no recorded exchange on the other channel -> wait is captured
+    calls.clear()
+    px._last = None
+    capturing["v"] = True
+    px.before_produce(0)
+    assert calls == [("cor_peer_wait_exit", 0)]
+    calls.clear()
+    px._last = 1                            # warm-up ended with a reduce: steady state, nothing to wait for
+    px.before_produce(0)
+    assert calls == []
