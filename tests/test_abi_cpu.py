@@ -144,3 +144,28 @@ def test_hooks_install_into_the_real_reference():
         hooks.uninstall()
     assert ref_lf.wbce_with_wiou_loss is orig
     assert ref_ma.MaskedPooling.forward is not hooks._masked_forward
+
+
+def test_argument_validation_fails_before_any_launch(lib):
+    """Bad arguments come back as COR_EINVAL (-1) with a message, before the library touches a device: the error
+    behaviour a binding in another host language would rely on (INTEGRATION.md contract)."""
+    EINVAL = -1
+    null = ctypes.c_void_p(None)
+    one = ctypes.c_void_p(16)          # any non-null value: validation must reject the call before dereferencing it
+    cases = [
+        ("cor_peer_gather_rows", (null, one, 1024, one, one, 0, 2, 0, null)),            # null source table
+        ("cor_peer_gather_rows", (one, one, 1000, one, one, 0, 2, 0, null)),             # bytes not a multiple of 16
+        ("cor_peer_gather_rows", (one, one, 1024, one, one, 3, 2, 0, null)),             # rank outside the world
+        ("cor_peer_reduce_rows", (one, one, 1024, one, one, 0, 64, 1, null)),            # world beyond cor_peer_max_world()
+        ("cor_peer_signal", (one, one, 0, 2, 5, null)),                                  # channel out of range
+        ("cor_infonce_tail", (null, 4, 16, one, one, one, 8, 4, 64, 1.0, one, one, one, null, null, 0.0, 0.0, 0.0, null, null)),
+        ("cor_infonce_tail", (one, 4, 16, one, one, one, 8, 4, 64, 1.0, one, one, one, null, null, 0.0, 0.0, 0.0, one, null)),  # total without seg/fgbg
+        ("cor_infonce_coef", (one, one, one, 0, 8, 1.0, one, 1.0, one, null)),           # no queries
+        ("cor_sim_lse_parts", (0, one, one, 8, 4, 64, 1.0, one, None, None, null)),      # nowhere to report the layout
+        ("cor_topk", (one, one, one, 8, 4, 64, 9, one, one, null)),                      # k > Nr
+    ]
+    for name, args in cases:
+        rc = getattr(lib, name)(*args)
+        assert rc == EINVAL, (name, rc)
+        assert lib.cor_last_error(), name
+    assert lib.cor_peer_max_world() >= 8 and lib.cor_peer_flag_bytes() >= 4 * 2 * 2 * 8 and lib.cor_peer_state_bytes() >= 16
