@@ -169,3 +169,22 @@ def test_argument_validation_fails_before_any_launch(lib):
         assert rc == EINVAL, (name, rc)
         assert lib.cor_last_error(), name
     assert lib.cor_peer_max_world() >= 8 and lib.cor_peer_flag_bytes() >= 4 * 2 * 2 * 8 and lib.cor_peer_state_bytes() >= 16
+
+
+def test_header_is_plain_c_and_a_c_host_can_bind_it(lib, tmp_path):
+    """include/cor_b200.h compiles as C99 (not only as C++) and a C program linked against the library can call it."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "c_abi_probe")
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_abi_probe.c"),
+           "-L", libdir, "-l:libcor_b200.so", f"-Wl,-rpath,{libdir}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "ABI v1" in r.stdout and "-> -1" in r.stdout
