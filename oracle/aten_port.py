@@ -1,7 +1,8 @@
 """CPU port of the reference region path on the same ATen op sequence (torch, differentiable).
 
 TEST INFRASTRUCTURE ONLY (see oracle/np_oracle.py header): imported by tests/, smoke() and the
-``cpu_baseline`` / ``--impl reference`` legs of bench.py, never by ``cor_b200/``.
+``cpu_baseline`` / ``torch_eager_gpu`` / ``--impl reference`` baseline legs of bench.py (as the thing the product is
+compared WITH, never as the thing measured as ours), never by ``cor_b200/``.
 
 Why a second oracle: the reference is Python and cannot travel to the GPU box, and the numpy
 restatement (np_oracle.py) is single-threaded and has no autograd.  This port issues the same
