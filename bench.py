@@ -29,9 +29,37 @@ import torch  # noqa: E402
 METRIC = "region_scored_triplets_per_sec"
 UNIT = "triplets/s"
 CFG = dict(B=16, M=64, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, tau=0.07)
-# dram__bytes_read.sum + dram__bytes_write.sum per mask_prep_kernel launch from the committed ncu --set full capture
-# (profiles/): filled in from the capture of the SAME configuration, else null.
-TRAFFIC_NCU = {"f32": 4304488392, "u8": None}   # profiles/r01_step_kernels_ncu_full_summary.csv: 4.295021 GB read + 9.467 MB written
+
+
+def traffic_from_profiles(cfg, mask_dtype, kernel="mask_prep"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, READ AT RUN TIME from the newest
+    committed `ncu --set full` summary under profiles/ whose name carries this configuration's key
+    (`..._B{B}_M{M}_{dtype}...csv`); the round-1 capture (no key in its name) is config 2 with fp32 masks.  None when no
+    capture of this configuration is committed -- a stale constant could not reveal a regression."""
+    import csv
+    import glob
+    key = f"_B{cfg['B']}_M{cfg['M']}_{mask_dtype}"
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*ncu_full*{key}*.csv")), reverse=True)
+    if not cands and (cfg["B"], cfg["M"], mask_dtype) == (16, 64, "f32"):
+        cands = [os.path.join(ROOT, "profiles", "r01_step_kernels_ncu_full_summary.csv")]
+    for path in cands:
+        try:
+            with open(path, newline="") as f:
+                for row in csv.DictReader(f):
+                    if kernel not in row.get("Kernel Name", ""):
+                        continue
+                    tot = 0.0
+                    for col, val in row.items():
+                        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                            if col.startswith(name):
+                                unit = col[col.find("[") + 1:col.find("]")].lower() if "[" in col else "byte"
+                                mul = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+                                tot += float(val) * mul
+                    if tot > 0:
+                        return int(tot), os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
 
 
 _T0 = time.perf_counter()
@@ -44,11 +72,13 @@ def trace(msg):
 
 
 def peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, bf16 TFLOP/s burst, source)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))), "measured"
-    return 6650.0, 1590.0, "fallback"
+        burst = float(p.get("bf16_tflops", 1590.0))
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", burst)), burst, "measured"
+    return 6650.0, 1590.0, 1590.0, "fallback"
 
 
 # ------------------------------------------------------------------------------------------ inputs
@@ -125,13 +155,30 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------- CPU baseline leg
-def cpu_port_step(sample, tau):
-    """One fwd+bwd of the same step on the host cores through the ATen port of the reference."""
-    from oracle import aten_port as ap
+def cpu_kind():
+    """"reference": oracle/_ref holds the reference's own modules (oracle/build_ref.py copied them, sha256 verified);
+    "port": it does not travel with this snapshot and the ATen port stands in."""
+    from oracle import ref_step
+    return "reference" if (ref_step.available() and ref_step.verified()) else "port"
+
+
+def cpu_port_step(sample, tau, kind=None):
+    """One fwd+bwd of the same step on the host cores: through the reference's own functions (oracle/_ref) when they are
+    there, else through the ATen port of the reference."""
     p, e, c = (sample[k].detach().clone().requires_grad_(True) for k in ("pred", "emb", "comb"))
-    loss, _ = ap.region_step_loss(p, e, c, sample["masks"], tau=tau)
+    if (kind or cpu_kind()) == "reference" and not p.is_cuda:
+        from oracle import ref_step
+        loss, _ = ref_step.region_step_loss(p, e, c, sample["masks"], tau=tau)
+    else:
+        from oracle import aten_port as ap
+        loss, _ = ap.region_step_loss(p, e, c, sample["masks"], tau=tau)
     loss.backward()
     return float(loss.detach())
+
+
+def cpu_what(kind):
+    return ("reference functions utils/loss_func.py (oracle/_ref, unmodified copy) + Class-N InfoNCE restatement" if kind == "reference"
+            else "oracle/aten_port.py = reference ATen op sequence (oracle/_ref absent)")
 
 
 def cpu_baseline(inputs_cpu, cfg, triplets, iters, warm=1):
@@ -146,9 +193,10 @@ def cpu_baseline(inputs_cpu, cfg, triplets, iters, warm=1):
         cpu_port_step(sample, cfg["tau"])
         ts.append(time.perf_counter() - t0)
     med = sorted(ts)[len(ts) // 2]
-    return {"value": triplets / med, "unit": UNIT, "cores": cores, "kind": "port",
+    kind = cpu_kind()
+    return {"value": triplets / med, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{triplets} triplets x {cfg['M']} masks {cfg['H']}x{cfg['W']} fp32, fwd+bwd, median of {iters} after {warm} warm-up "
-                      f"({med * 1e3:.0f} ms/step); oracle/aten_port.py = reference ATen op sequence"}, med
+                      f"({med * 1e3:.0f} ms/step); {cpu_what(kind)}"}, med
 
 
 def torch_eager_gpu_baseline(inp, cfg, iters=5, warm=2):
@@ -185,10 +233,11 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    triplets = args.cpu_triplets
+    triplets = min(args.cpu_triplets, cfg["B"])
     host = device_inputs(torch.device("cpu"), 1234, dict(cfg, B=triplets), "f32")
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
+    kind = cpu_kind()
     sample = {k: v.float() for k, v in host.items()}
     for _ in range(args.warmup):
         cpu_port_step(sample, cfg["tau"])
@@ -201,9 +250,10 @@ def run_reference(args, cfg):
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, args, sample_triplets=triplets),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"each step = {triplets} triplets x {cfg['M']} masks (bounded sample of the {cfg['B']}-triplet batch), "
-                                       "reference ATen op sequence (oracle/aten_port.py; the reference is Python and cannot travel)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": (f"each step = the whole {cfg['B']}-triplet batch x {cfg['M']} masks" if triplets == cfg["B"] else
+                                        f"each step = {triplets} triplets x {cfg['M']} masks (bounded sample of the {cfg['B']}-triplet batch)")
+                                       + f", fwd+bwd; {cpu_what(kind)}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit_result(line)
 
@@ -224,38 +274,175 @@ def workload_config(cfg, args, sample_triplets=None):
          "mask_size": [cfg["H"], cfg["W"]], "mask_dtype": args.mask_dtype, "tau": cfg["tau"], "backward": True,
          "emb_grad": True, "negatives": _negatives_note(),
          "l2": "inputs (>= 1 GiB of masks per step) exceed the 126 MB L2; no explicit flush"}
-    if sample_triplets is not None:
+    if sample_triplets is not None and sample_triplets != cfg["B"]:
         c["cpu_sample_triplets"] = sample_triplets
     return c
 
 
 # --------------------------------------------------------------------------------------------- main
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa(local):
-    """Multi-rank e2e leg: run this rank (and first-touch its pinned staging buffers) on the CPUs NVML reports as local
-    to its GPU, so that eight ranks do not all push their H2D copies through one socket.  Returns the number of CPUs
-    bound to, or None when nothing changed (single socket, cgroup without those CPUs, NVML unavailable)."""
+    """Multi-rank e2e leg: run this rank (and first-touch its pinned staging buffers, which are allocated AFTER this call)
+    on the CPUs local to its GPU, so that eight ranks do not all push their H2D copies through one socket.  The CPU set
+    comes from NVML's affinity mask, else from sysfs (/sys/bus/pci/devices/<bdf>/{local_cpulist,numa_node}).  Returns
+    a dict {"cpus": n bound to (None = unchanged), "numa_node": node or None, "how": source}."""
+    info = {"cpus": None, "numa_node": None, "how": None}
     if os.environ.get("COR_BENCH_NUMA", "1") == "0":
-        return None
+        return info
+    allowed = os.sched_getaffinity(0)
+    local_cpus = set()
+    bdf = None
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        pass
     try:
         import pynvml
-        import torch
         pynvml.nvmlInit()
-        pr = torch.cuda.get_device_properties(local)
         try:
-            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("0000" + bdf).encode()) if bdf else pynvml.nvmlDeviceGetHandleByIndex(local)
         except Exception:
             h = pynvml.nvmlDeviceGetHandleByIndex(local)
         n = os.cpu_count() or 1
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
         local_cpus = {i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1}
-        allowed = os.sched_getaffinity(0)
-        use = local_cpus & allowed
-        if not use or use == allowed:
-            return None
-        os.sched_setaffinity(0, use)
-        return len(use)
+        info["how"] = "nvml"
     except Exception:
-        return None
+        local_cpus = set()
+    if bdf:
+        base = f"/sys/bus/pci/devices/{bdf}"
+        try:
+            node = int(open(base + "/numa_node").read().strip())
+            info["numa_node"] = node if node >= 0 else None
+        except Exception:
+            pass
+        if not local_cpus or local_cpus >= allowed:
+            try:
+                local_cpus = _parse_cpulist(open(base + "/local_cpulist").read())
+                info["how"] = "sysfs local_cpulist"
+            except Exception:
+                pass
+        if (not local_cpus or local_cpus >= allowed) and info["numa_node"] is not None:
+            try:
+                local_cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{info['numa_node']}/cpulist").read())
+                info["how"] = "sysfs node cpulist"
+            except Exception:
+                pass
+    use = local_cpus & allowed
+    if not use or use == allowed:
+        return info
+    try:
+        os.sched_setaffinity(0, use)
+        info["cpus"] = len(use)
+    except Exception:
+        pass
+    return info
+
+
+def pcie_h2d_gbs(dev, nbytes=1 << 30, iters=3):
+    """A bare pinned-host -> device cudaMemcpyAsync of `nbytes`, timed with CUDA events (best of `iters`): the platform
+    ceiling of the e2e leg on this GPU's PCIe link.  Every rank runs it at the same time (the caller barriers first), so
+    at N > 1 the figure includes whatever the host side loses to sharing."""
+    src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    src.fill_(1)                       # first touch on this rank's (NUMA-bound) CPUs
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(iters + 1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+    del src, dst
+    return best
+
+
+def l2_flush(buf):
+    buf.add_(1)                         # 256 MiB read + written: nothing of the previous launch stays in the 126 MB L2
+
+
+def secondary_tensor_lines(dev, tc_burst, hbm_peak, iters=10):
+    """Driver-run lines for the kernels the 16-query step does not exercise at their design point:
+    the tcgen05 similarity / InfoNCE kernel at config 4's global shape (1024 queries x 102 400 regions x 256), its
+    few-query shape (16 x 102 400, HBM-bound), InfoNCE forward+backward at the global shape, and config 3's top-k
+    (256 x 4096, k = 10).  CUDA events around each launch, L2 flushed before every timed launch."""
+    from cor_b200 import ops
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(99)
+    Nr, D = 102400, 256
+    r32 = torch.nn.functional.normalize(torch.randn(Nr, D, device=dev, generator=g), dim=-1)
+    r16 = r32.bfloat16()
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)
+
+    def timed(fn, n=iters):
+        ts = []
+        for i in range(n + 2):
+            l2_flush(flush)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2], ts[0]
+
+    for Nq in (1024, 16):
+        q16 = torch.nn.functional.normalize(torch.randn(Nq, D, device=dev, generator=g), dim=-1).bfloat16()
+        try:
+            med, best = timed(lambda: ops._sim_lse_parts(r16, q16, 1.0 / 0.07, "umma"))
+            flops = 2.0 * Nq * Nr * D
+            byts = (Nq + Nr) * D * 2
+            tf_s = flops / (med * 1e-3) / 1e12
+            gb_s = byts / (med * 1e-3) / 1e9
+            bound = "tensor" if Nq >= 256 else "hbm"
+            out[f"sim_umma_kernel_{Nq}x{Nr}"] = {
+                "what": "similarity + online log-sum-exp (InfoNCE forward), S never written; one launch", "bound": bound, "ms": med, "ms_best": best,
+                "flops": flops, "algorithmic_bytes": byts, "achieved_tflops": tf_s, "achieved_gbs": gb_s,
+                "peak": tc_burst if bound == "tensor" else hbm_peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                "frac": (tf_s / tc_burst) if bound == "tensor" else (gb_s / hbm_peak),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if bound == "tensor" else "MEASURED_PEAKS.json hbm_gbs"}
+        except Exception as e:  # noqa: BLE001
+            out[f"sim_umma_kernel_{Nq}x{Nr}"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        Nq = 1024
+        q32 = torch.nn.functional.normalize(torch.randn(Nq, D, device=dev, generator=g), dim=-1)
+        tg = (torch.arange(Nq, device=dev) * 97) % Nr
+
+        def fwd_bwd():
+            r = r32.detach().requires_grad_(True)
+            q = q32.detach().requires_grad_(True)
+            ops.infonce_loss(r, q, tg, tau=0.07, regions_bf16=r16).backward()
+
+        med, best = timed(fwd_bwd, n=5)
+        out["infonce_fwd_bwd_1024x102400"] = {"what": "InfoNCE value + dQ + dR through the public op (includes its bf16 casts and launches)",
+                                              "ms": med, "ms_best": best, "flops": 8.0 * Nq * Nr * D,
+                                              "achieved_tflops": 8.0 * Nq * Nr * D / (med * 1e-3) / 1e12}
+    except Exception as e:  # noqa: BLE001
+        out["infonce_fwd_bwd_1024x102400"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:
+        gal = r32[:4096].contiguous()
+        qs = torch.nn.functional.normalize(torch.randn(256, D, device=dev, generator=g), dim=-1)
+        med, best = timed(lambda: ops.topk_retrieve(gal, qs, 10))
+        out["topk_256x4096_k10"] = {"what": "BASELINE configs[2]: similarity + radix select + exact re-score + sort (public op)", "ms": med,
+                                    "ms_best": best, "queries_per_s": 256 / (med * 1e-3)}
+    except Exception as e:  # noqa: BLE001
+        out["topk_256x4096_k10"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    del flush
+    torch.cuda.empty_cache()
+    return out
 
 
 _RESULT_FD = None
@@ -291,12 +478,13 @@ def main():
     ap_.add_argument("--mask-dtype", default="f32", choices=["f32", "u8"])
     ap_.add_argument("--batch", type=int, default=CFG["B"])
     ap_.add_argument("--masks", type=int, default=CFG["M"])
-    ap_.add_argument("--cpu-triplets", type=int, default=1, help="triplets per CPU-baseline step (bounded sample)")
+    ap_.add_argument("--cpu-triplets", type=int, default=16, help="triplets per CPU-baseline step (default: the whole 16-triplet batch)")
     ap_.add_argument("--cpu-iters", type=int, default=3)
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     ap_.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap_.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     ap_.add_argument("--no-u8-variant", action="store_true", help="skip the extra uint8-mask leg reported under 'variants'")
+    ap_.add_argument("--no-secondary", action="store_true", help="skip the extra tensor-core / top-k kernel lines (N=1 only)")
     ap_.add_argument("--pool-engine", default="auto")
     ap_.add_argument("--sim-engine", default="auto")
     args = ap_.parse_args()
@@ -319,7 +507,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's banner off stdout (env beats /etc/nccl.conf)
         dist.init_process_group("nccl", device_id=dev)
     trace("init done")
-    hbm_peak, tc_peak, peak_kind = peaks()
+    hbm_peak, tc_peak, tc_burst, peak_kind = peaks()
 
     inp = device_inputs(dev, 1234 + rank, cfg, args.mask_dtype)
     trace("inputs ready")
@@ -404,8 +592,9 @@ def main():
     dom = max(per_kernel, key=per_kernel.get)
     prep_ms = per_kernel.get("cor_mask_prep", 0.0) / max(1, calls.get("cor_mask_prep", 1))
     achieved = prep_bytes / (prep_ms * 1e-3) / 1e9 if prep_ms > 0 else 0.0
+    traffic, traffic_src = traffic_from_profiles(cfg, args.mask_dtype)
     roofline = {"kernel": "mask_prep_kernel (cor_mask_prep)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": TRAFFIC_NCU.get(args.mask_dtype), "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": prep_bytes, "ms_per_launch": prep_ms,
                 "share_of_kernel_time": per_kernel.get("cor_mask_prep", 0.0) / max(1e-9, sum(per_kernel.values())),
                 "dominant_by_events": dom, "timed": "CUDA events around the C-ABI call, eager pass over the same K steps"}
@@ -429,7 +618,14 @@ def main():
 
     trace("e2e")
     # ---- end to end through the public API with host buffers (H2D of the step's inputs + D2H of the loss)
-    numa_cpus = bind_to_gpu_numa(local) if world > 1 else None
+    numa = bind_to_gpu_numa(local) if world > 1 else {"cpus": None, "numa_node": None, "how": None}
+    # platform ceiling of this leg: a bare pinned H2D copy on every GPU at once (same NUMA binding, same moment)
+    barrier()
+    pcie = torch.tensor([pcie_h2d_gbs(dev)], device=dev)
+    pcie_all = [pcie.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(pcie_all, pcie)
+    pcie_all = [round(float(x), 2) for x in pcie_all]
     host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in inp.items()}
     for k in host:
         host[k].copy_(inp[k])
@@ -455,7 +651,7 @@ def main():
     # ---- variant (reported, not the headline): the same masks shipped as uint8 -- bit-identical values after the
     #      kernel's /255 (what an 8-bit PNG holds before ToTensor, utils/dataloader.py:190), a quarter of the bytes
     variants = {}
-    if args.mask_dtype == "f32" and not args.no_u8_variant and world == 1:
+    if args.mask_dtype == "f32" and not args.no_u8_variant:     # every rank runs it symmetrically (the step gathers negatives at N > 1)
         try:
             inp8 = dict(inp, masks=(inp["masks"] * 255).to(torch.uint8))
             b8 = region.StepBuffers(cfg["B"], cfg["M"], cfg["C"], cfg["h"], cfg["w"], cfg["H"], cfg["W"], cfg["hp"], cfg["wp"], device=dev,
@@ -463,23 +659,33 @@ def main():
             b8.load(inp8)
             b8.capture(backward=True, emb_grad=True, warmup=2, **kw)
             torch.cuda.synchronize()
+            barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(args.steps):
                 b8.replay()
             a1.record()
-            torch.cuda.synchronize()
-            ms8 = a0.elapsed_time(a1) / args.steps
+            barrier()
+            ms8 = torch.tensor([a0.elapsed_time(a1) / args.steps], device=dev)
             host8 = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True).copy_(v) for k, v in inp8.items()}
             torch.cuda.synchronize()
             b8.run(host8, **kw)
+            barrier()
             t8 = time.perf_counter()
             for _ in range(e2e_steps):
                 b8.run(host8, **kw)
-            torch.cuda.synchronize()
-            w8 = (time.perf_counter() - t8) / e2e_steps
-            variants["u8_masks"] = {"value": cfg["B"] / (ms8 * 1e-3), "ms_per_step": ms8, "e2e": {"value": cfg["B"] / w8, "unit": UNIT,
-                                    "h2d_bytes_per_step": b8.h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": w8 * 1e3}}
+            barrier()
+            w8 = torch.tensor([(time.perf_counter() - t8) / e2e_steps], device=dev)
+            if world > 1:
+                dist.all_reduce(ms8, op=dist.ReduceOp.MAX)
+                dist.all_reduce(w8, op=dist.ReduceOp.MAX)
+            ms8, w8 = float(ms8), float(w8)
+            variants["u8_masks"] = {"what": "same step, masks shipped as uint8 (the 8-bit PNG bytes before ToTensor, utils/dataloader.py:187-197); "
+                                            "the kernel's x/255 reproduces ToTensor bit for bit",
+                                    "value": cfg["B"] * world / (ms8 * 1e-3), "ms_per_step": ms8,
+                                    "e2e": {"value": cfg["B"] * world / w8, "unit": UNIT, "h2d_bytes_per_step": b8.h2d_bytes,
+                                            "d2h_bytes_per_step": 4, "ms_per_step": w8 * 1e3}}
+            b8.graph = None
             del b8, host8, inp8
         except Exception as e:   # the variant must never take the headline down with it
             variants["u8_masks"] = {"error": f"{type(e).__name__}: {e}"}
@@ -488,6 +694,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         trace("torch eager on the GPU")
         eager_gpu = torch_eager_gpu_baseline(inp, cfg)
+    if rank == 0 and world == 1 and not args.no_secondary:
+        trace("secondary kernel lines")
+        del inp
+        torch.cuda.empty_cache()
+        secondary.update(secondary_tensor_lines(dev, tc_burst, hbm_peak))
 
     trace("done")
     if rank == 0:
@@ -495,7 +706,10 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": workload_config(cfg, args), "clocks": clk.summary(),
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": bufs.h2d_bytes, "d2h_bytes_per_step": 4,
-                        "ms_per_step": float(e2e_ms), "steps": e2e_steps, "numa_local_cpus": numa_cpus},
+                        "ms_per_step": float(e2e_ms), "steps": e2e_steps, "numa_local_cpus": numa["cpus"], "numa_node": numa["numa_node"],
+                        "numa_how": numa["how"], "pcie_gbs_per_gpu": pcie_all,
+                        "pcie_note": "bare pinned cudaMemcpyAsync H2D of 1 GiB on every GPU at once (best of 3): the platform ceiling of this leg",
+                        "pcie_bound_ms_per_step": bufs.h2d_bytes / (min(pcie_all) * 1e9) * 1e3},
                 "gpu_launches": launches, "graphed": graphed, "roofline": roofline, "secondary_kernels": secondary, "variants": variants,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},
                 "loss": float(loss.detach())}

@@ -93,6 +93,7 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_peer_max_world", i)
         _sig(lib, "cor_peer_flag_bytes", sz)
         _sig(lib, "cor_peer_state_bytes", sz)
+        _sig(lib, "cor_peer_error_word", i)
         _sig(lib, "cor_peer_alloc", i, i, sz, pp)
         _sig(lib, "cor_peer_free", i, p)
         _sig(lib, "cor_peer_export", i, p, C.c_char_p)

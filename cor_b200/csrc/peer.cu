@@ -13,7 +13,11 @@
 // launches carry no per-step host state and replay inside a CUDA graph.  enter(e): "what I produced for step e is
 // in my buffer" (stream order put the producer kernel before this one); exit(e): "I have finished reading yours" -
 // a rank leaves the kernel only after every peer has signalled exit(e), hence the next step's producer kernel may
-// overwrite the buffer.  Waits are bounded (~20 s of globaltimer) and trap instead of hanging the box.
+// overwrite the buffer.  Waits are bounded by COR_PEER_TIMEOUT_S of globaltimer (default 600 s, 0 = wait for ever):
+// on expiry the kernel does NOT trap (that would take the whole CUDA context with it, where the NCCL pair this
+// replaces would simply have blocked through a slow rank's checkpoint save) -- it records the epoch in the local
+// error word (state[kErrWord]) and carries on; the host raises CorError from PeerExchange.check().
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,7 +27,8 @@ namespace cor {
 constexpr int kPeerMaxWorld = 16;
 constexpr int kPeerThreads = 512;
 constexpr int kPeerCtas = 64;
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+constexpr int kStateWords = 4;
+constexpr int kErrWord = 2 * kStateWords;       // state[8]: 0, or 0x80000000 | epoch of the first wait that expired
 
 // flags block of one rank: [channel][phase][source rank]
 __device__ __forceinline__ unsigned* flag_slot(unsigned* flags, int channel, int phase, int src) {
@@ -49,23 +54,23 @@ __device__ __forceinline__ unsigned long long now_ns() {
   return t;
 }
 
-__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch) {
+struct PeerCtl {
+  unsigned* const* flags;   // device array [world]: every rank's flag block (entry `rank` is the local one)
+  unsigned* state;          // local: [channel] {epoch done, CTA counter, epoch signalled, -}, then the error word
+  int rank, world, channel;
+  unsigned long long timeout_ns;   // 0 = no limit
+};
+
+__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned epoch, const PeerCtl& c) {
   const unsigned long long t0 = now_ns();
   while ((int)(ld_acquire_sys(p) - epoch) < 0) {
     __nanosleep(64);
-    if (now_ns() - t0 > kPeerTimeoutNs) {
-      printf("cor_b200 peer exchange: timed out waiting for a peer (epoch %u)\n", epoch);
-      __trap();
+    if (c.timeout_ns && now_ns() - t0 > c.timeout_ns) {
+      atomicCAS(&c.state[kErrWord], 0u, 0x80000000u | epoch);     // first failure wins; the host reports it
+      return;
     }
   }
 }
-
-struct PeerCtl {
-  unsigned* const* flags;   // device array [world]: every rank's flag block (entry `rank` is the local one)
-  unsigned* state;          // local: [channel] {epoch done, CTA counter, epoch signalled, -}
-  int rank, world, channel;
-};
-constexpr int kStateWords = 4;
 
 // "What I produced for my next epoch on this channel is in my buffer": one tiny CTA right after the producer kernel,
 // so that whatever the stream runs between this and the exchange kernel hides the skew between the ranks.
@@ -83,13 +88,13 @@ __global__ void peer_signal_kernel(PeerCtl c) {
 // Before the producer overwrites the buffer: every peer has finished reading what the last exchange published.
 __global__ void peer_wait_exit_kernel(PeerCtl c) {
   const unsigned done = c.state[kStateWords * c.channel];
-  if (threadIdx.x < c.world) wait_flag(flag_slot(c.flags[c.rank], c.channel, 1, threadIdx.x), done);
+  if (threadIdx.x < c.world) wait_flag(flag_slot(c.flags[c.rank], c.channel, 1, threadIdx.x), done, c);
 }
 
 // Every CTA waits until all peers have signalled the epoch this launch serves.
 __device__ __forceinline__ unsigned peer_enter(const PeerCtl& c) {
   const unsigned epoch = c.state[kStateWords * c.channel] + 1u;
-  if (threadIdx.x < c.world) wait_flag(flag_slot(c.flags[c.rank], c.channel, 0, threadIdx.x), epoch);
+  if (threadIdx.x < c.world) wait_flag(flag_slot(c.flags[c.rank], c.channel, 0, threadIdx.x), epoch, c);
   __syncthreads();
   return epoch;
 }
@@ -193,7 +198,8 @@ extern "C" {
 
 int cor_peer_max_world(void) { return kPeerMaxWorld; }
 size_t cor_peer_flag_bytes(void) { return sizeof(unsigned) * 2 * 2 * kPeerMaxWorld; }
-size_t cor_peer_state_bytes(void) { return sizeof(unsigned) * 2 * kStateWords; }
+size_t cor_peer_state_bytes(void) { return sizeof(unsigned) * (2 * kStateWords + 4); }
+int cor_peer_error_word(void) { return kErrWord; }
 
 int cor_peer_alloc(int device, size_t bytes, void** ptr) {
   COR_REQUIRE(ptr && bytes > 0, "cor_peer_alloc: bad arguments");
@@ -247,12 +253,23 @@ int cor_peer_close(void* ptr) {
   return COR_OK;
 }
 
+// COR_PEER_TIMEOUT_S: seconds a wait may last before the error word is set (default 600; 0 = unbounded)
+static unsigned long long peer_timeout_ns() {
+  static unsigned long long cached = ~0ull;
+  if (cached == ~0ull) {
+    double s = 600.0;
+    if (const char* e = getenv("COR_PEER_TIMEOUT_S")) s = atof(e);
+    cached = s <= 0.0 ? 0ull : (unsigned long long)(s * 1e9);
+  }
+  return cached;
+}
+
 static int peer_ctl(const char* what, void* const* peer_flags, void* state, int rank, int world, int channel, PeerCtl* c) {
   COR_REQUIRE(peer_flags && state, "%s: null pointer", what);
   COR_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "%s: rank %d / world %d (max %d)", what, rank, world,
               kPeerMaxWorld);
   COR_REQUIRE(channel == 0 || channel == 1, "%s: channel %d", what, channel);
-  *c = PeerCtl{reinterpret_cast<unsigned* const*>(peer_flags), reinterpret_cast<unsigned*>(state), rank, world, channel};
+  *c = PeerCtl{reinterpret_cast<unsigned* const*>(peer_flags), reinterpret_cast<unsigned*>(state), rank, world, channel, peer_timeout_ns()};
   return COR_OK;
 }
 
@@ -279,7 +296,7 @@ int cor_peer_gather_rows(const void* const* peer_src, void* all, long long bytes
               world, kPeerMaxWorld);
   COR_REQUIRE(channel == 0 || channel == 1, "cor_peer_gather_rows: channel %d", channel);
   COR_REQUIRE(bytes_per_rank > 0 && bytes_per_rank % 16 == 0 && (uintptr_t)all % 16 == 0, "cor_peer_gather_rows: %lld bytes per rank must be a positive multiple of 16, 16-byte aligned", bytes_per_rank);
-  PeerCtl c{reinterpret_cast<unsigned* const*>(peer_flags), reinterpret_cast<unsigned*>(state), rank, world, channel};
+  PeerCtl c{reinterpret_cast<unsigned* const*>(peer_flags), reinterpret_cast<unsigned*>(state), rank, world, channel, peer_timeout_ns()};
   const long long vecs = bytes_per_rank / 16;
   peer_gather_kernel<<<peer_grid(vecs * world), kPeerThreads, 0, as_stream(stream)>>>(reinterpret_cast<const uint4* const*>(peer_src),
                                                                                      reinterpret_cast<uint4*>(all), vecs, c);
@@ -293,7 +310,7 @@ int cor_peer_reduce_rows(const void* const* peer_src, float* out, long long floa
               world, kPeerMaxWorld);
   COR_REQUIRE(channel == 0 || channel == 1, "cor_peer_reduce_rows: channel %d", channel);
   COR_REQUIRE(floats_per_rank > 0 && floats_per_rank % 4 == 0 && (uintptr_t)out % 16 == 0, "cor_peer_reduce_rows: %lld floats per rank must be a positive multiple of 4, 16-byte aligned", floats_per_rank);
-  PeerCtl c{reinterpret_cast<unsigned* const*>(peer_flags), reinterpret_cast<unsigned*>(state), rank, world, channel};
+  PeerCtl c{reinterpret_cast<unsigned* const*>(peer_flags), reinterpret_cast<unsigned*>(state), rank, world, channel, peer_timeout_ns()};
   const long long vecs = floats_per_rank / 4;
   peer_reduce_kernel<<<peer_grid(vecs), kPeerThreads, 0, as_stream(stream)>>>(reinterpret_cast<const uint4* const*>(peer_src),
                                                                              reinterpret_cast<float4*>(out), vecs, c);

@@ -8,10 +8,16 @@ Differences from the reference that callers can observe:
     device; when no sample is valid the returned zero still carries a (zero) grad_fn instead of being
     a grad-less ``torch.tensor(0.0)``;
   * ``fg_feat_similarity_loss`` and ``bg_feat_similarity_loss`` called back to back on the same
-    tensors (utils/trainer_v3_g.py:69-71) share ONE pass over the feature map and the mask.
+    tensors (utils/trainer_v3_g.py:69-71) share ONE pass over the feature map and the mask.  The half
+    that was not asked for is parked (per thread) until the matching call consumes it; it is dropped as
+    soon as the first result dies or a backward runs through it, so a caller that only ever uses one of
+    the two keeps no graph alive beyond its own result.  The match is by tensor identity and
+    ``_version``: inputs refilled behind autograd's back (CUDA-graph replay, raw memcpy) are not seen as
+    changed -- such callers should use ``fg_bg_feat_similarity_loss`` / ``region_path_loss`` directly.
 """
 from __future__ import annotations
 
+import threading
 import weakref
 
 import torch
@@ -44,7 +50,7 @@ def mask_pooling(embeddings: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     return ops.region_pool(embeddings, mask, transform=ops.W_CLAMP, normalize=True, engine="stream").fg
 
 
-_memo = {}
+_memo = threading.local()          # .entry = (key, which, pair): one parked half per thread
 
 
 def _same_call(entry, tensors):
@@ -71,13 +77,27 @@ def _shared(query_image_embeddings, comb_support_feat, query_mask, which: int):
     runs the fused pass and parks the other half for the second.  The parked entry is keyed on the
     identity (weakref) and version of the tensor objects and is consumed by the matching call."""
     tensors = (query_image_embeddings, comb_support_feat, query_mask)
-    hit = _memo.pop("entry", None)
+    hit = getattr(_memo, "entry", None)
+    _memo.entry = None
     if hit is not None and hit[1] != which and _same_call(hit, tensors):
         return hit[2][which]
     pair = fg_bg_feat_similarity_loss(*tensors)
     key = (tuple(weakref.ref(t) for t in tensors), tuple(t._version for t in tensors), torch.is_grad_enabled())
-    _memo["entry"] = (key, which, pair)
-    return pair[which]
+    entry = (key, which, pair)
+    _memo.entry = entry
+    out = pair[which]
+
+    def drop(*_):
+        if getattr(_memo, "entry", None) is entry:
+            _memo.entry = None
+
+    # the parked half shares the pooling node with ``out``: once a backward has gone through ``out`` (its buffers are
+    # freed) or ``out`` itself is gone, the other half must be recomputed rather than served from the memo
+    if out.requires_grad:
+        out.register_hook(lambda g: drop())
+    out = out.view_as(out)            # a fresh tensor object whose lifetime is the caller's: finalizer below
+    weakref.finalize(out, drop)
+    return out
 
 
 def fg_feat_similarity_loss(query_image_embeddings, comb_support_feat, query_mask) -> torch.Tensor:

@@ -90,16 +90,17 @@ class PeerExchange:
                     break
                 self.mapped.append(p.value)
                 ptrs.append(p.value)
-        flag = torch.tensor([1 if good else 0], device=self.device, dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        if int(flag.item()) == 0:
+        votes = [None] * self.world          # object collective: works over NCCL and over gloo (one-GPU emulation in the tests)
+        dist.all_gather_object(votes, bool(good), group=group)
+        if not all(votes):
             self.close()
             return
         i64 = dict(dtype=torch.int64, device=self.device)
         self.flag_ptrs = torch.tensor(ptrs, **i64)
         self.pub_ptrs = torch.tensor([p + self.off_pub for p in ptrs], **i64)
         self.gall_ptrs = torch.tensor([p + self.off_gall for p in ptrs], **i64)
-        self.state = torch.zeros(max(lib.cor_peer_state_bytes() // 4, 8), dtype=torch.int32, device=self.device)
+        self.state = torch.zeros(max(lib.cor_peer_state_bytes() // 4, 12), dtype=torch.int32, device=self.device)
+        self._err_word = lib.cor_peer_error_word()
         self._raw = _Raw(self.base, self.nbytes)
         whole = torch.as_tensor(self._raw, device=self.device)
         self.pub = whole[self.off_pub:self.off_pub + n_local * Cc * 2].view(torch.bfloat16).view(n_local, Cc)
@@ -116,10 +117,19 @@ class PeerExchange:
     def before_produce(self, channel: int):
         """Call before the kernel that overwrites ``pub`` (channel 0) / ``gall`` (channel 1).  The peers have provably
         finished reading the previous contents once an exchange on the OTHER channel ran in between (its enter barrier
-        orders them); only when the same channel is used twice in a row is a wait kernel needed."""
-        capturing = torch.cuda.is_current_stream_capturing()
-        if self._last == channel or (capturing and self._last != 1 - channel):
+        orders them); only when the same channel is used twice in a row is a wait kernel needed.  That shortcut rests
+        on host-side history, which a CUDA graph would freeze: a captured step ALWAYS carries the wait (one 32-thread
+        CTA polling local flags), so that eager forward-only calls between replays cannot tear the rows."""
+        if self._last == channel or torch.cuda.is_current_stream_capturing():
             self._ctl("cor_peer_wait_exit", channel)
+
+    def check(self):
+        """Raise CorError if any wait of this exchange expired (COR_PEER_TIMEOUT_S).  Synchronises the device: call it
+        where the step already syncs (``StepBuffers.run`` does), not inside a captured region."""
+        word = int(self.state[self._err_word].item()) & 0xFFFFFFFF
+        if word:
+            raise L.CorError(f"peer exchange: rank {self.rank} gave up waiting for a peer at epoch {word & 0x7FFFFFFF} "
+                             "(COR_PEER_TIMEOUT_S); results since then are invalid")
 
     def signal(self, channel: int):
         """Call right after the producer kernel: tells the peers this rank's buffer is ready for the next exchange."""
@@ -161,14 +171,21 @@ def get_exchange(n_local: int, Cc: int, device, group=None) -> Optional[PeerExch
     first use per shape."""
     if not enabled() or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
-    if dist.get_backend(group) != "nccl":
-        return None
+    if dist.get_backend(group) != "nccl" and os.environ.get("COR_PEER_ANY_BACKEND", "0") != "1":
+        return None       # gloo plumbing is only for the one-GPU emulation of the peer test
     key = (n_local, Cc, torch.device(device).index, id(group))
     px = _CACHE.get(key)
     if px is None:
         px = PeerExchange(n_local, Cc, torch.device(device), group)
         _CACHE[key] = px
     return px if px.ok else None
+
+
+def check_all():
+    """``PeerExchange.check`` on every live exchange."""
+    for px in _CACHE.values():
+        if px.ok:
+            px.check()
 
 
 def release_all():

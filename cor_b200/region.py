@@ -77,8 +77,7 @@ def _target_rows(dev, B, M, offset):
     key = (dev.index, B, M, offset)
     t = _target_cache.get(key)
     if t is None:
-        if len(_target_cache) > 64:
-            _target_cache.clear()
+        # never evicted (a few bytes each): captured graphs hold the raw pointer
         t = torch.arange(B, device=dev, dtype=torch.int64) * M + offset
         _target_cache[key] = t
     return t
@@ -115,6 +114,8 @@ class _FusedStepFn(torch.autograd.Function):
         B, M = masks.shape[:2]
         Cc, h, w = emb.shape[1:]
         P = h * w
+        if masks.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
+            masks = masks.float()            # bool / fp16 / fp64 masks: one conversion serves mask_prep and the seg loss
         emb_c = emb.contiguous()
         pred_c = ops._as_supported_float(pred)
         comb_c = comb.reshape(B, -1).float().contiguous()
@@ -357,6 +358,9 @@ def region_step(pred: torch.Tensor, emb: torch.Tensor, comb: torch.Tensor, masks
     B, M = masks.shape[:2]
     if comb.shape[0] != B or emb.shape[0] != B or pred.shape[0] != B:
         raise CorError("region_step: batch sizes differ")
+    if comb.numel() != B * emb.shape[1]:
+        raise CorError(f"region_step: comb {tuple(comb.shape)} must hold one row of C={emb.shape[1]} channels per triplet "
+                       "(the kernels read the queries with the feature map's row width)")
     if fused and _fused_ok(emb, masks, pool_engine) and pred.dim() == 4 and pred.shape[1] == 1:
         loss, out8, out4, nce, fg = _FusedStepFn.apply(pred, emb, comb, masks, float(tau), float(nce_weight), bool(gather), sim_engine,
                                                        int(bg_mode), 5.0, 5.0)
@@ -385,7 +389,9 @@ class StepBuffers:
 
     def __init__(self, B, M, C=256, h=64, w=64, H=1024, W=1024, hp=256, wp=256, D=None, device="cuda",
                  emb_dtype=torch.bfloat16, mask_dtype=torch.float32):
-        D = C if D is None else D
+        if D is not None and D != C:
+            raise CorError(f"StepBuffers: the composed query width D={D} must equal the feature channels C={C}")
+        D = C
         self.device = torch.device(device)
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.device)
         self.d = {"pred": mk((B, 1, hp, wp), emb_dtype), "emb": mk((B, C, h, w), emb_dtype), "comb": mk((B, 1, D), torch.float32),
@@ -446,4 +452,6 @@ class StepBuffers:
             loss, self.grads = self._step(backward, emb_grad, kw)
         self.loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if peer._CACHE:
+            peer.check_all()             # a peer wait that expired (COR_PEER_TIMEOUT_S) invalidates the step: raise
         return float(self.loss_host)

@@ -242,7 +242,10 @@ int cor_soft_metrics(const float* pred, const void* gt, int gt_dtype, float gt_s
  *   cor_peer_alloc/free: a zero-filled cudaMalloc region on `device`; cor_peer_export: its 64-byte CUDA IPC handle;
  *   cor_peer_open/close: map a peer's region into this process (peer access enabled lazily).
  *   flags: every rank sets aside cor_peer_flag_bytes() of its region (zeroed), peers signal into it; state:
- *   cor_peer_state_bytes() of LOCAL zeroed memory (epoch + CTA counter per channel).
+ *   cor_peer_state_bytes() of LOCAL zeroed memory (epoch + CTA counter per channel, then one error word).
+ *   Waits last at most COR_PEER_TIMEOUT_S seconds (environment, default 600, 0 = unbounded); an expired wait does not
+ *   trap: it stores 0x80000000|epoch in state[cor_peer_error_word()] and the kernel carries on with stale data, so
+ *   the host must check that word before trusting a step (cor_b200.peer.PeerExchange.check()).
  *   peer_src / peer_flags: DEVICE arrays [world] of pointers (entry `rank` = the local buffer).
  *   cor_peer_gather_rows:  all[p*bytes : (p+1)*bytes] = peer_src[p][0 : bytes]   for every rank p
  *   cor_peer_reduce_rows:  out[i] = sum_p peer_src[p][rank*floats + i], p ascending (deterministic)
@@ -251,11 +254,12 @@ int cor_soft_metrics(const float* pred, const void* gt, int gt_dtype, float gt_s
  *   cor_peer_wait_exit: "every peer has finished reading what my last exchange on `channel` published" - needed
  *                       before the producer only when no exchange on the other channel ran since (cor_b200/peer.py)
  *   The exchanges wait for all peers' signal, pull, and post their own exit flag.  Epochs live in device memory:
- *   graph-capturable; every rank must issue the same sequence; a wait that exceeds ~20 s traps instead of hanging.
+ *   graph-capturable; every rank must issue the same sequence.
  * ---------------------------------------------------------------------------------------------- */
 int cor_peer_max_world(void);
 size_t cor_peer_flag_bytes(void);
 size_t cor_peer_state_bytes(void);
+int cor_peer_error_word(void);   /* index (in u32 words) of the error word inside `state`: non-zero = a wait expired */
 int cor_peer_alloc(int device, size_t bytes, void** ptr);
 int cor_peer_free(void* ptr);
 int cor_peer_export(void* ptr, unsigned char* handle64);

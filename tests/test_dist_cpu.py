@@ -118,8 +118,9 @@ def test_peer_exchange_steps_aside_without_nccl(monkeypatch):
 
 def test_peer_exchange_wait_policy(monkeypatch):
     """Host-side half of the peer protocol (cor_b200/peer.py): a wait_exit kernel is issued before a producer only when
-    no exchange on the OTHER channel ran since the last one on this channel (or, while capturing a CUDA graph, whenever
-    that cannot be proven from the recorded sequence).  Every exchange needs exactly one signal before it."""
+    no exchange on the OTHER channel ran since the last one on this channel -- or ALWAYS while capturing a CUDA graph,
+    because the host-side history would be frozen into the graph and an eager forward-only call between replays would
+    break it.  Every exchange needs exactly one signal before it."""
     from cor_b200 import peer
     px = object.__new__(peer.PeerExchange)
     px._last = None
@@ -143,13 +144,11 @@ def test_peer_exchange_wait_policy(monkeypatch):
     px.before_produce(0); exchange(0)
     px.before_produce(0); exchange(0)
     assert calls == [("cor_peer_wait_exit", 0)]
-    # capture: first producer of the graph with no recorded exchange on the other channel -> wait is captured
-    calls.clear()
-    px._last = None
-    capturing["v"] = True
-    px.before_produce(0)
-    assert calls == [("cor_peer_wait_exit", 0)]
-    calls.clear()
-    px._last = 1                            # warm-up ended with a reduce: steady state, nothing to wait for
-    px.before_produce(0)
-    assert calls == []
+    # capture: the wait is always part of the graph, whatever ran before the capture
+    for last in (None, 0, 1):
+        calls.clear()
+        px._last = last
+        capturing["v"] = True
+        px.before_produce(0)
+        px.before_produce(1)
+        assert calls == [("cor_peer_wait_exit", 0), ("cor_peer_wait_exit", 1)]

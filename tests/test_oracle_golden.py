@@ -137,3 +137,26 @@ def test_vailder_offline_binarisation():
     out = no.vailder_postprocess(g["pred"], tuple(int(v) for v in g["gt_hw"]))
     close(out, g["resized"], rtol=1e-5, atol=2e-6)
     assert (no.binarize(out) == g["hard"]).mean() >= 0.999
+
+
+def test_reference_copy_step_equals_port():
+    """oracle/_ref (the reference's own modules, copied by oracle/build_ref.py) composed into the bench step equals the
+    ATen port: the two CPU baselines of bench.py are interchangeable, value and gradients."""
+    import pytest
+    import torch
+    from cor_b200 import synth
+    from oracle import aten_port as ap
+    from oracle import ref_step
+    if not ref_step.available():
+        pytest.skip("oracle/_ref not built (no reference checkout on this machine)")
+    assert ref_step.verified(), "oracle/_ref differs from its MANIFEST"
+    d = synth.make_triplets(5, B=3, M=4, C=32, h=16, w=16, H=64, W=64, hp=32, wp=32)
+    grads = []
+    for fn in (ref_step.region_step_loss, ap.region_step_loss):
+        t = {k: torch.from_numpy(v).clone().requires_grad_(k != "masks") for k, v in d.items()}
+        loss, rows = fn(t["pred"], t["emb"], t["comb"], t["masks"], tau=0.07)
+        loss.backward()
+        grads.append((float(loss), rows.detach(), t["pred"].grad, t["emb"].grad, t["comb"].grad))
+    assert abs(grads[0][0] - grads[1][0]) < 1e-6 * abs(grads[1][0])
+    for a, b in zip(grads[0][1:], grads[1][1:]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
