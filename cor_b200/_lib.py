@@ -14,6 +14,9 @@ LIB_PATH = os.path.join(HERE, "libcor_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "cor_b200.h")
 
 F32, BF16, U8 = 0, 1, 2
+ABI_VERSION = 2
+# terms of the segmentation loss (include/cor_b200.h COR_SEG_*)
+SEG_WBCE, SEG_WIOU, SEG_DICE, SEG_BCE, SEG_IOU, SEG_WDICE, SEG_FOCAL, SEG_NTERMS = range(8)
 W_PLAIN, W_CLAMP, W_SIGMOID = 0, 1, 2
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8}
@@ -73,8 +76,10 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_fgbg_loss_bwd", i, p, ll, p, ll, p, ll, i, i, i, p, p, p, ll, f, f, p, ll, i, p, ll, p, ll, i, p)
         _sig(lib, "cor_step_combine", i, p, p, p, f, f, f, p, p)
         _sig(lib, "cor_seg_loss_work_bytes", sz, i, i, i)
-        _sig(lib, "cor_seg_loss_fwd", i, p, i, p, i, f, i, i, i, i, i, ll, f, f, f, f, f, p, p, p, p, p, p)
-        _sig(lib, "cor_seg_loss_bwd", i, p, i, p, p, p, i, i, i, f, f, p, p, i, p)
+        _sig(lib, "cor_seg_loss_npartials", i)
+        fp = C.POINTER(C.c_float)
+        _sig(lib, "cor_seg_loss_fwd", i, p, i, p, i, f, i, i, i, i, i, ll, fp, f, f, f, p, p, p, p, p, p)
+        _sig(lib, "cor_seg_loss_bwd", i, p, i, p, p, p, i, i, i, fp, f, f, f, p, p, i, p)
         _sig(lib, "cor_sim_work_bytes", sz, i, i, i)
         _sig(lib, "cor_sim_stream_fwd", i, p, p, i, i, i, f, p, p, p, p)
         _sig(lib, "cor_sim_umma_fwd", i, p, p, i, i, i, f, p, p, p, p)
@@ -103,8 +108,8 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_peer_wait_exit", i, p, p, i, i, i, p)
         _sig(lib, "cor_peer_gather_rows", i, p, p, ll, p, p, i, i, i, p)
         _sig(lib, "cor_peer_reduce_rows", i, p, p, ll, p, p, i, i, i, p)
-        if lib.cor_abi_version() != 1:
-            raise CorError(f"ABI version mismatch: library {lib.cor_abi_version()}, binding 1")
+        if lib.cor_abi_version() != ABI_VERSION:
+            raise CorError(f"ABI version mismatch: library {lib.cor_abi_version()}, binding {ABI_VERSION}; rebuild with `python -m cor_b200.build`")
         _lib = lib
         return lib
 

@@ -6,7 +6,13 @@
 // separable sliding-window sums in shared memory, and the per-pixel terms are reduced in registers ->
 // warp shuffles -> one partial record per tile.  Compulsory HBM traffic only: logits once, the mask
 // sectors the taps touch once; ~15 full passes over [B,1,256,256] in the eager reference become one.
-#include "common.cuh"
+//
+// Two forward kernels share the per-pixel arithmetic (seg_common.cuh): the row-strip streaming kernel of seg_strip.cu
+// serves the shapes the reference produces (target at the logit size, or a mask at exactly 4x it); this file's 64x64
+// tile kernel serves every other resample ratio, wide images and oddly aligned buffers.
+#include <stdlib.h>
+
+#include "seg_common.cuh"
 
 namespace cor {
 
@@ -15,7 +21,6 @@ constexpr int kHalo = 15;         // (31-1)/2
 constexpr int kTH = kT + 2 * kHalo;   // 94
 constexpr int kTS = kTH + 1;      // padded row stride (odd -> conflict-free column walks)
 constexpr int kHS = kT + 1;
-constexpr int kNP = 8;            // partial sums per tile
 constexpr int kSegThreads = 512;  // 64 columns x 8 row segments of 8 rows
 constexpr int kRowsPT = kT / (kSegThreads / 64);   // rows per thread in step 3
 
@@ -127,7 +132,6 @@ __global__ void __launch_bounds__(kSegThreads) seg_loss_tile_kernel(const TP* __
   {
     const int x = px, y0 = py0;
     const int gx = tx0 + x;
-    const bool want_focal = focal_gamma >= 0.f;
     float s = 0.f;
 #pragma unroll
     for (int d = 0; d < 31; ++d) s += sm.hs[(y0 + d) * kHS + x];
@@ -140,24 +144,8 @@ __global__ void __launch_bounds__(kSegThreads) seg_loss_tile_kernel(const TP* __
       const int gy = ty0 + y0 + y;
       if (gy < H && gx < W) {
         const float t = sm.t[(y0 + y + kHalo) * kTS + x + kHalo];
-        const float wgt = 1.f + 5.f * fabsf(s * (1.f / 961.f) - t);
-        const float zz = z[y];
-        const float e = __expf(-fabsf(zz));
-        const float bce = (1.f - t) * zz - (fminf(zz, 0.f) - __logf(1.f + e));   // (1-t)x - logsigmoid(x)
-        const float inv = __fdividef(1.f, 1.f + e);
-        const float p = zz >= 0.f ? inv : e * inv;
-        f[0] += wgt;
-        f[1] = fmaf(wgt, bce, f[1]);
-        f[2] = fmaf(p * t, wgt, f[2]);
-        f[3] = fmaf(p + t, wgt, f[3]);
-        f[4] = fmaf(p, t, f[4]);
-        f[5] += p;
-        f[6] += t;
-        if (want_focal) {
-          const float pt = p * t + (1.f - p) * (1.f - t);
-          const float at = focal_alpha * t + (1.f - focal_alpha) * (1.f - t);
-          f[7] = fmaf(at * __powf(fmaxf(1.f - pt, 0.f), focal_gamma), bce, f[7]);
-        }
+        float wgt;
+        seg_pixel_terms(z[y], t, s, focal_alpha, focal_gamma, f, wgt);
         if (t_save) {
           const long long o = ((long long)n * H + gy) * W + gx;
           t_save[o] = t;
@@ -176,54 +164,68 @@ __global__ void __launch_bounds__(kSegThreads) seg_loss_tile_kernel(const TP* __
   }
 }
 
-// per_sample[n][8] = tile sums in fixed order; out8 = {loss, dice, focal, mean wbce, mean wiou, 0,0,0}
-__global__ void __launch_bounds__(256) seg_loss_finalize_kernel(const double* __restrict__ part, int N, int tiles, int HW, float w1,
-                                                                float w2, float dice_smooth, float* __restrict__ per_sample,
+// The seven per-sample loss terms (seg_common.cuh) from the per-sample sums, in double.
+__device__ __forceinline__ void seg_terms(const double* s, double HW, double sm, double (&T)[kNC]) {
+  T[0] = s[1] / s[0];
+  T[1] = 1.0 - (s[2] + 1e-6) / (s[3] - s[2] + 1e-6);
+  T[2] = 1.0 - (2.0 * s[4] + sm) / (s[5] + s[6] + sm);
+  T[3] = s[8] / HW;
+  T[4] = 1.0 - (s[4] + 1e-6) / (s[5] + s[6] - s[4] + 1e-6);
+  T[5] = 1.0 - (2.0 * s[2] + sm) / (s[3] + sm);
+  T[6] = s[7] / HW;
+}
+
+// per_sample[n][kNP] = tile / strip sums in fixed order; out8 = {loss, dice, focal, wbce, wiou, bce, iou, wdice}, each the
+// mean over samples, loss = mean_n sum_k coef[k] term_k[n]
+__global__ void __launch_bounds__(256) seg_loss_finalize_kernel(const double* __restrict__ part, int N, int tiles, int HW, SegCoef coef,
+                                                                float dice_smooth, float* __restrict__ per_sample,
                                                                 float* __restrict__ out8) {
-  __shared__ double scratch[5 * 32];
-  __shared__ double ssum[32][kNP];          // per-sample tile sums for a batch of 32 samples
-  double v[5] = {0, 0, 0, 0, 0};
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    // thread (s, k) = (sample n0 + tid / 8, partial k = tid % 8) folds the tiles in fixed order
-    const int sidx = threadIdx.x >> 3, k = threadIdx.x & 7, n = n0 + sidx;
-    double acc = 0.0;
-    if (n < N)
-      for (int t = 0; t < tiles; ++t) acc += part[((long long)n * tiles + t) * kNP + k];
-    ssum[sidx][k] = acc;
-    if (n < N) per_sample[(long long)n * kNP + k] = (float)acc;
+  __shared__ double scratch[8 * 32];
+  __shared__ double ssum[16][kNP + 1];      // per-sample sums for a batch of 16 samples
+  double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int n0 = 0; n0 < N; n0 += 16) {
+    // thread (s, k) = (sample n0 + tid / 16, partial k = tid % 16) folds the tiles in fixed order
+    const int sidx = threadIdx.x >> 4, k = threadIdx.x & 15, n = n0 + sidx;
+    if (k < kNP) {
+      double acc = 0.0;
+      if (n < N)
+        for (int t = 0; t < tiles; ++t) acc += part[((long long)n * tiles + t) * kNP + k];
+      ssum[sidx][k] = acc;
+      if (n < N) per_sample[(long long)n * kNP + k] = (float)acc;
+    }
     __syncthreads();
-    if (threadIdx.x < 32 && n0 + threadIdx.x < N) {
-      const double* s = ssum[threadIdx.x];
-      const double wbce = s[1] / s[0];
-      const double inter = s[2], uni = s[3] - s[2];
-      const double wiou = 1.0 - (inter + 1e-6) / (uni + 1e-6);
-      v[0] += (double)w1 * wbce + (double)w2 * wiou;
-      v[1] += 1.0 - (2.0 * s[4] + dice_smooth) / (s[5] + s[6] + dice_smooth);
-      v[2] += s[7];
-      v[3] += wbce;
-      v[4] += wiou;
+    if (threadIdx.x < 16 && n0 + threadIdx.x < N) {
+      double T[kNC];
+      seg_terms(ssum[threadIdx.x], (double)HW, (double)dice_smooth, T);
+      double l = 0.0;
+#pragma unroll
+      for (int c = 0; c < kNC; ++c) l += (double)coef.c[c] * T[c];
+      v[0] += l;
+      v[1] += T[2]; v[2] += T[6]; v[3] += T[0]; v[4] += T[1]; v[5] += T[3]; v[6] += T[4]; v[7] += T[5];
     }
     __syncthreads();
   }
-  block_sum<5>(v, scratch);
+  block_sum<8>(v, scratch);
   if (threadIdx.x == 0) {
-    out8[0] = (float)(v[0] / N);
-    out8[1] = (float)(v[1] / N);
-    out8[2] = (float)(v[2] / ((double)N * HW));
-    out8[3] = (float)(v[3] / N);
-    out8[4] = (float)(v[4] / N);
-    out8[5] = out8[6] = out8[7] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out8[k] = (float)(v[k] / N);
   }
 }
 
-// d loss / d pred, elementwise (4 pixels per thread).
+// d loss / d pred, elementwise.  With p = sigmoid(z), dp = p(1-p) and the per-sample sums s[]:
+//   wbce: w (p - t) / s0                       bce: (p - t) / HW
+//   ratio terms 1 - A/B:  -(dA B - A dB)/B^2 dp   with (dA, dB) per pixel = wiou (t w, w - t w... see below)
+//   focal: a_t [ (1-p_t)^g (p - t) - g (1-p_t)^(g-1) (2t-1) dp bce ] / HW,  p_t = p t + (1-p)(1-t)
 template <typename TP, typename TG>
 __global__ void __launch_bounds__(256) seg_loss_bwd_kernel(const TP* __restrict__ pred, const float* __restrict__ t_save,
                                                            const float* __restrict__ w_save, const float* __restrict__ per_sample,
-                                                           int N, long long HW, float w1, float w2, const float* __restrict__ g_loss,
-                                                           TG* __restrict__ g_pred) {
+                                                           int N, long long HW, SegCoef coef, float dice_smooth, float focal_alpha,
+                                                           float focal_gamma, const float* __restrict__ g_loss, TG* __restrict__ g_pred) {
   const long long total = (long long)N * HW;
   const float g = g_loss[0] / (float)N;
+  const float c0 = coef.c[0], c1 = coef.c[1], c2 = coef.c[2], c3 = coef.c[3], c4 = coef.c[4], c5 = coef.c[5], c6 = coef.c[6];
+  const bool extras = c2 != 0.f || c3 != 0.f || c4 != 0.f || c5 != 0.f || c6 != 0.f;
+  const float inv_hw = 1.f / (float)HW;
   for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(o / HW);
     const float* s = per_sample + (long long)n * kNP;
@@ -231,9 +233,36 @@ __global__ void __launch_bounds__(256) seg_loss_bwd_kernel(const TP* __restrict_
     const float z = to_f<TP>(pred[o]), t = t_save[o], w = w_save[o];
     const float e = expf(-fabsf(z));
     const float p = z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    const float dp = p * (1.f - p);
     const float dwbce = w * (p - t) / sw;
     const float dratio = (t * w * U - I * w * (1.f - t)) / (U * U);   // d (I/U) / d p
-    g_pred[o] = from_f<TG>(g * (w1 * dwbce - w2 * dratio * p * (1.f - p)));
+    float d = c0 * dwbce - c1 * dratio * dp;
+    if (extras) {
+      const float sm = dice_smooth;
+      if (c2 != 0.f) {           // dice: A = 2 s4 + sm, B = s5 + s6 + sm; dA = 2t, dB = 1
+        const float A = 2.f * s[4] + sm, B = s[5] + s[6] + sm;
+        d -= c2 * (2.f * t * B - A) / (B * B) * dp;
+      }
+      if (c3 != 0.f) d += c3 * (p - t) * inv_hw;
+      if (c4 != 0.f) {           // iou: A = s4 + eps, B = s5 + s6 - s4 + eps; dA = t, dB = 1 - t
+        const float A = s[4] + 1e-6f, B = s[5] + s[6] - s[4] + 1e-6f;
+        d -= c4 * (t * B - A * (1.f - t)) / (B * B) * dp;
+      }
+      if (c5 != 0.f) {           // wdice: A = 2 s2 + sm, B = s3 + sm; dA = 2 t w, dB = w
+        const float A = 2.f * s[2] + sm, B = s[3] + sm;
+        d -= c5 * (2.f * t * w * B - A * w) / (B * B) * dp;
+      }
+      if (c6 != 0.f) {
+        const float bce = (1.f - t) * z - (fminf(z, 0.f) - log1pf(e));
+        const float pt = p * t + (1.f - p) * (1.f - t);
+        const float at = focal_alpha * t + (1.f - focal_alpha) * (1.f - t);
+        const float om = fmaxf(1.f - pt, 0.f);
+        const float pw = powf(om, focal_gamma);
+        const float dpw = om > 0.f ? focal_gamma * powf(om, focal_gamma - 1.f) : 0.f;
+        d += c6 * at * (pw * (p - t) - dpw * (2.f * t - 1.f) * dp * bce) * inv_hw;
+      }
+    }
+    g_pred[o] = from_f<TG>(g * d);
   }
 }
 
@@ -263,14 +292,23 @@ static int launch_tiles(const void* pred, const void* mask, float mscale, int N,
 
 using namespace cor;
 
+extern "C" int cor_seg_loss_npartials(void) { return kNP; }
+
 extern "C" size_t cor_seg_loss_work_bytes(int N, int H, int W) {
-  return (size_t)N * ceil_div(H, kT) * ceil_div(W, kT) * kNP * sizeof(double);
+  const int tiles = ceil_div(H, kT) * ceil_div(W, kT), strips = seg_strip_max_strips(H);
+  return (size_t)N * (tiles > strips ? tiles : strips) * kNP * sizeof(double);
+}
+
+static SegCoef make_coef(const float* coef7) {
+  SegCoef c;
+  for (int k = 0; k < kNC; ++k) c.c[k] = coef7 ? coef7[k] : (k < 2 ? 1.f : 0.f);    // default: wbce + wiou (loss_func.py:31)
+  return c;
 }
 
 extern "C" int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* mask, int mask_dtype, float mask_scale, int N,
-                                int H, int W, int Hm, int Wm, long long mask_nstride, float w1, float w2, float focal_alpha, float focal_gamma,
-                                float dice_smooth, float* out8, float* per_sample, float* t_save, float* w_save, void* work,
-                                cor_stream_t stream) {
+                                int H, int W, int Hm, int Wm, long long mask_nstride, const float* coef7, float focal_alpha,
+                                float focal_gamma, float dice_smooth, float* out8, float* per_sample, float* t_save, float* w_save,
+                                void* work, cor_stream_t stream) {
   COR_REQUIRE(pred && mask && out8 && per_sample && work, "cor_seg_loss_fwd: null pointer");
   COR_REQUIRE(N > 0 && H > 0 && W > 0 && Hm > 0 && Wm > 0, "cor_seg_loss_fwd: bad shape");
   COR_REQUIRE((t_save == nullptr) == (w_save == nullptr), "cor_seg_loss_fwd: t_save and w_save go together");
@@ -279,29 +317,41 @@ extern "C" int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* ma
   int rc = COR_EINVAL;
   if (mask_nstride <= 0) mask_nstride = (long long)Hm * Wm;
   COR_REQUIRE(mask_nstride >= (long long)Hm * Wm, "cor_seg_loss_fwd: mask_nstride too small");
+  const SegCoef coef = make_coef(coef7);
+  if (coef.c[6] == 0.f && focal_gamma >= 0.f && coef7) focal_gamma = -1.f;     // nobody asked for the focal term: skip its powf
+  int tiles = 0;
+  const char* knob = getenv("COR_SEG_STRIP");                                  // A/B knob, read per call
+  const bool no_strip = knob && atoi(knob) == 0;
+  rc = no_strip ? COR_EINVAL
+                : seg_strip_try_launch(pred, pred_dtype, mask, mask_dtype, mask_scale, N, H, W, Hm, Wm, mask_nstride, focal_alpha,
+                                       focal_gamma, t_save, w_save, part, &tiles, st);
+  if (rc == COR_ECUDA) return rc;
+  if (rc != COR_OK) {
+    tiles = ceil_div(H, kT) * ceil_div(W, kT);
 #define COR_SEG(TP, TM) rc = launch_tiles<TP, TM>(pred, mask, mask_scale, N, H, W, Hm, Wm, mask_nstride, focal_alpha, focal_gamma, t_save, w_save, part, st)
-  if (pred_dtype == COR_F32 && mask_dtype == COR_F32) COR_SEG(float, float);
-  else if (pred_dtype == COR_BF16 && mask_dtype == COR_F32) COR_SEG(bf16, float);
-  else if (pred_dtype == COR_F32 && mask_dtype == COR_U8) COR_SEG(float, uint8_t);
-  else if (pred_dtype == COR_BF16 && mask_dtype == COR_U8) COR_SEG(bf16, uint8_t);
-  else if (pred_dtype == COR_F32 && mask_dtype == COR_BF16) COR_SEG(float, bf16);
-  else if (pred_dtype == COR_BF16 && mask_dtype == COR_BF16) COR_SEG(bf16, bf16);
-  else COR_REQUIRE(false, "cor_seg_loss_fwd: unsupported dtypes pred=%d mask=%d", pred_dtype, mask_dtype);
+    if (pred_dtype == COR_F32 && mask_dtype == COR_F32) COR_SEG(float, float);
+    else if (pred_dtype == COR_BF16 && mask_dtype == COR_F32) COR_SEG(bf16, float);
+    else if (pred_dtype == COR_F32 && mask_dtype == COR_U8) COR_SEG(float, uint8_t);
+    else if (pred_dtype == COR_BF16 && mask_dtype == COR_U8) COR_SEG(bf16, uint8_t);
+    else if (pred_dtype == COR_F32 && mask_dtype == COR_BF16) COR_SEG(float, bf16);
+    else if (pred_dtype == COR_BF16 && mask_dtype == COR_BF16) COR_SEG(bf16, bf16);
+    else COR_REQUIRE(false, "cor_seg_loss_fwd: unsupported dtypes pred=%d mask=%d", pred_dtype, mask_dtype);
 #undef COR_SEG
-  if (rc) return rc;
-  const int tiles = ceil_div(H, kT) * ceil_div(W, kT);
-  seg_loss_finalize_kernel<<<1, 256, 0, st>>>(part, N, tiles, H * W, w1, w2, dice_smooth, per_sample, out8);
+    if (rc) return rc;
+  }
+  seg_loss_finalize_kernel<<<1, 256, 0, st>>>(part, N, tiles, H * W, coef, dice_smooth, per_sample, out8);
   return check_launch("seg_loss_finalize_kernel");
 }
 
 extern "C" int cor_seg_loss_bwd(const void* pred, int pred_dtype, const float* t_save, const float* w_save,
-                                const float* per_sample, int N, int H, int W, float w1, float w2, const float* g_loss,
-                                void* g_pred, int g_dtype, cor_stream_t stream) {
+                                const float* per_sample, int N, int H, int W, const float* coef7, float dice_smooth, float focal_alpha,
+                                float focal_gamma, const float* g_loss, void* g_pred, int g_dtype, cor_stream_t stream) {
   COR_REQUIRE(pred && t_save && w_save && per_sample && g_loss && g_pred, "cor_seg_loss_bwd: null pointer");
   const long long HW = (long long)H * W;
   const int blocks = (int)min((long long)sm_count() * 8, (N * HW + 255) / 256);
   cudaStream_t st = as_stream(stream);
-#define COR_SEGB(TP, TG) seg_loss_bwd_kernel<TP, TG><<<blocks, 256, 0, st>>>((const TP*)pred, t_save, w_save, per_sample, N, HW, w1, w2, g_loss, (TG*)g_pred)
+  const SegCoef coef = make_coef(coef7);
+#define COR_SEGB(TP, TG) seg_loss_bwd_kernel<TP, TG><<<blocks, 256, 0, st>>>((const TP*)pred, t_save, w_save, per_sample, N, HW, coef, dice_smooth, focal_alpha, focal_gamma, g_loss, (TG*)g_pred)
   if (pred_dtype == COR_F32 && g_dtype == COR_F32) COR_SEGB(float, float);
   else if (pred_dtype == COR_BF16 && g_dtype == COR_BF16) COR_SEGB(bf16, bf16);
   else if (pred_dtype == COR_BF16 && g_dtype == COR_F32) COR_SEGB(bf16, float);

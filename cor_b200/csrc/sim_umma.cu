@@ -35,6 +35,11 @@ constexpr int kSimBK = 64;
 constexpr int kSimABytes = kSimHalf * kSimBK * 2;  // 16 KB: one k-block of one query half
 constexpr int kSimBBytes = kSimBN * kSimBK * 2;    // 16 KB: one stage of regions
 constexpr int kSimMaxKB = 4;                       // D <= 256
+#ifndef COR_SIM_POLY_OF4
+#define COR_SIM_POLY_OF4 2                         // of every 4 element pairs, how many take the FMA-pipe exp2 (0 = all MUFU)
+#endif
+constexpr int kSimPolyOf4 = COR_SIM_POLY_OF4;
+static_assert(kSimBN == 128, "the epilogue is unrolled for four 32-column chunks");
 
 struct SimSmemTail {
   uint64_t qfull, full[kSimMaxStages], empty[kSimMaxStages], acc_full[2], acc_empty[2];
@@ -151,6 +156,93 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
       gscale = coef.g_loss[0] * coef.g_mul * inv_tau / (float)Nq;
       tq = coef.targets[q];
     }
+    // One 32-column chunk of this thread's query row (registers v[0..31] = S[q, r0+col .. +31]).
+    auto proc = [&](uint32_t (&v)[32], int r0, int col) {
+      const int nval = min(32, Nr - (r0 + col));
+      if (S && qok) {
+        float* dst = S + (long long)q * Nr + r0 + col;
+        if (vec_ok && nval == 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nval) dst[j] = __uint_as_float(v[j]);
+        }
+      }
+      if (want_coef && qok) {
+        bf16* dst = coef.P + (long long)q * Nr + r0 + col;
+        const long long hit = tq - (long long)(r0 + col);        // position of the target inside this chunk, if any
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float c0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c2, neg_lse2));
+          float c1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c2, neg_lse2));
+          if (hit == 2 * j) c0 -= 1.f;
+          if (hit == 2 * j + 1) c1 -= 1.f;
+          __nv_bfloat162 pk = __floats2bfloat162_rn(c0 * gscale, c1 * gscale);
+          w[j] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        if (pvec_ok && nval == 32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nval) {
+              const uint32_t u = w[j >> 1];
+              reinterpret_cast<uint16_t*>(dst)[j] = (uint16_t)((j & 1) ? (u >> 16) : (u & 0xffffu));
+            }
+        }
+      }
+      if (part) {
+        if (nval == 32) {
+          // Full chunk.  The MMA of a 128 x 128 x 256 tile and 16 384 MUFU.EX2 both take ~1024 SM cycles, so an
+          // all-MUFU epilogue paces the tensor pipe.  Here: max by 3-input FMNMX (16 ops), the exponent arguments by
+          // packed FFMA2, kSimPolyPairs of the 16 pairs through the FMA-pipe polynomial exp2 and the rest through
+          // MUFU, packed FADD2 accumulation in independent chains.
+          float t10[10];
+#pragma unroll
+          for (int j = 0; j < 10; ++j) t10[j] = max3(__uint_as_float(v[3 * j]), __uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2]));
+          const float u0 = max3(t10[0], t10[1], t10[2]), u1 = max3(t10[3], t10[4], t10[5]), u2 = max3(t10[6], t10[7], t10[8]);
+          const float u3 = max3(t10[9], __uint_as_float(v[30]), __uint_as_float(v[31]));
+          const float cm = fmaxf(max3(u0, u1, u2), u3);
+          if (cm > m) { ssum *= ex2_approx((m - cm) * c2); m = cm; }
+          const float mc = m * c2;
+          const uint64_t C2 = pack2(c2, c2), NM = pack2(-mc, -mc);
+          uint64_t a0 = 0ull, a1 = 0ull;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint64_t x2 = fma2(pack2u(v[2 * j], v[2 * j + 1]), C2, NM);
+            uint64_t e2;
+            if ((j % 4) < kSimPolyOf4) {        // spread the polynomial pairs evenly through the chunk
+              e2 = exp2_poly2(x2);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              e2 = pack2(ex2_approx(x0), ex2_approx(x1));
+            }
+            if (j & 1) a1 = add2(a1, e2);
+            else a0 = add2(a0, e2);
+          }
+          float s0, s1;
+          unpack2(add2(a0, a1), s0, s1);
+          ssum += s0 + s1;
+        } else {
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nval) cm = fmaxf(cm, __uint_as_float(v[j]));
+          if (cm > m) { ssum *= ex2_approx((m - cm) * c2); m = cm; }
+          const float mc = m * c2;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nval) ssum += ex2_approx(fmaf(__uint_as_float(v[j]), c2, -mc));
+        }
+      }
+    };
     int i = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
@@ -159,87 +251,31 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
       if (active) {
         const int r0 = t * kSimBN;
         const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)((buf * 2 + hf) * kSimBN);
-        for (int col = 0; col < kSimBN; col += 32) {
-          if (r0 + col >= Nr) break;               // warp-uniform: whole chunk out of range
-          uint32_t v[32];
-          tmem_ld_32(taddr + (uint32_t)col, v);
-          tmem_ld_wait();
-          const int nval = min(32, Nr - (r0 + col));
-          if (S && qok) {
-            float* dst = S + (long long)q * Nr + r0 + col;
-            if (vec_ok && nval == 32) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nval) dst[j] = __uint_as_float(v[j]);
-            }
-          }
-          if (want_coef && qok) {
-            bf16* dst = coef.P + (long long)q * Nr + r0 + col;
-            const long long hit = tq - (long long)(r0 + col);        // position of the target inside this chunk, if any
-            uint32_t w[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float c0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), c2, neg_lse2));
-              float c1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), c2, neg_lse2));
-              if (hit == 2 * j) c0 -= 1.f;
-              if (hit == 2 * j + 1) c1 -= 1.f;
-              __nv_bfloat162 pk = __floats2bfloat162_rn(c0 * gscale, c1 * gscale);
-              w[j] = *reinterpret_cast<uint32_t*>(&pk);
-            }
-            if (pvec_ok && nval == 32) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nval) {
-                  const uint32_t u = w[j >> 1];
-                  reinterpret_cast<uint16_t*>(dst)[j] = (uint16_t)((j & 1) ? (u >> 16) : (u & 0xffffu));
-                }
-            }
-          }
-          if (part) {
-            if (nval == 32) {
-              // full chunk: max tree, then 4 independent exp2/add chains (1 FFMA + 1 MUFU + 1 FADD per element)
-              float t8[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                t8[j] = fmaxf(fmaxf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
-                              fmaxf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-              const float cm = fmaxf(fmaxf(fmaxf(t8[0], t8[1]), fmaxf(t8[2], t8[3])), fmaxf(fmaxf(t8[4], t8[5]), fmaxf(t8[6], t8[7])));
-              if (cm > m) { ssum *= ex2_approx((m - cm) * c2); m = cm; }
-              const float mc = m * c2;
-              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                a0 += ex2_approx(fmaf(__uint_as_float(v[4 * j]), c2, -mc));
-                a1 += ex2_approx(fmaf(__uint_as_float(v[4 * j + 1]), c2, -mc));
-                a2 += ex2_approx(fmaf(__uint_as_float(v[4 * j + 2]), c2, -mc));
-                a3 += ex2_approx(fmaf(__uint_as_float(v[4 * j + 3]), c2, -mc));
-              }
-              ssum += (a0 + a1) + (a2 + a3);
-            } else {
-              float cm = -INFINITY;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nval) cm = fmaxf(cm, __uint_as_float(v[j]));
-              if (cm > m) { ssum *= ex2_approx((m - cm) * c2); m = cm; }
-              const float mc = m * c2;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nval) ssum += ex2_approx(fmaf(__uint_as_float(v[j]), c2, -mc));
-            }
-          }
-        }
+        // chunk c+1 is in flight (tcgen05.ld) while chunk c is processed; columns beyond Nr hold zeros (TMA fills
+        // out-of-range region rows), loading them is harmless and proc() masks them
+        const int nch = min(kSimBN / 32, (Nr - r0 + 31) / 32);       // warp-uniform
+        uint32_t va[32], vb[32];
+        tmem_ld_32(taddr, va);
+        tmem_ld_wait();
+        if (nch > 1) tmem_ld_32(taddr + 32u, vb);
+        proc(va, r0, 0);
+        tmem_ld_wait();
+        if (nch > 2) tmem_ld_32(taddr + 64u, va);
+        if (nch > 1) proc(vb, r0, 32);
+        tmem_ld_wait();
+        if (nch > 3) tmem_ld_32(taddr + 96u, vb);
+        if (nch > 2) proc(va, r0, 64);
+        tmem_ld_wait();
+        // the accumulator is in registers: hand the TMEM buffer back BEFORE the last chunk is processed
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
+        if (nch > 3) proc(vb, r0, 96);
+      } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->acc_empty[buf]);
     }
     if (part && active) {
       float* o = part + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * kSimBM + hf * kSimHalf + qd * 32 + lane) * 2;

@@ -60,6 +60,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D / 4-D tiled loads (no swizzle): the segmentation-loss strip kernel streams mask-row bands and logit rows with these.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
+      : "memory");
+}
+
 // One slice of a stage, delivered to the same shared-memory offset of EVERY CTA in `mask` (and signalling the
 // mbarrier at the same offset in each of them): the cluster fetches the tile from L2 once.
 __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask,
@@ -163,6 +178,60 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs (FFMA2 / FADD2: two lanes of work per issue slot) and 3-input max (FMNMX3) ----
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// 2^x for a PAIR of arguments x <= 0 on the FMA pipe (no MUFU): Cody-Waite split x = n + f, n = round(x) taken from the
+// low mantissa bits of x + 1.5*2^23, 2^f on [-0.5, 0.5] by a degree-5 minimax polynomial (max relative error 2.4e-7, the
+// same as ex2.approx), then n added into the exponent field.  Arguments below -126 are clamped (result ~1e-38).
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t magic = pack2(12582912.f, 12582912.f);
+  const uint64_t t2 = add2(x2, magic);
+  const uint64_t f2 = sub2(x2, sub2(t2, magic));
+  uint64_t p2 = pack2(0x1.5c08e4p-10f, 0x1.5c08e4p-10f);
+  p2 = fma2(p2, f2, pack2(0x1.3d0c52p-7f, 0x1.3d0c52p-7f));
+  p2 = fma2(p2, f2, pack2(0x1.c6b6e4p-5f, 0x1.c6b6e4p-5f));
+  p2 = fma2(p2, f2, pack2(0x1.ebf918p-3f, 0x1.ebf918p-3f));
+  p2 = fma2(p2, f2, pack2(0x1.62e428p-1f, 0x1.62e428p-1f));
+  p2 = fma2(p2, f2, pack2(0x1.000002p+0f, 0x1.000002p+0f));
+  const uint32_t r0 = (uint32_t)p2 + ((uint32_t)t2 << 23);
+  const uint32_t r1 = (uint32_t)(p2 >> 32) + ((uint32_t)(t2 >> 32) << 23);
+  return pack2u(r0, r1);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -176,6 +245,10 @@ __device__ __forceinline__ bool elect_one() {
 // ---- host: tensor-map encoder (driver entry point fetched at run time; no libcuda link) ------------
 // 2-D bf16 row-major [rows, cols] with a [box_rows, 64] box and 128B swizzle.
 int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
+// General tiled map, no swizzle, zero fill outside the tensor: `rank` dims (fastest first) of `elem_bytes`-sized elements
+// (1 = u8, 2 = bf16, 4 = f32), byte strides for dims 1..rank-1 (multiples of 16), box extents per dim (<= 256 each).
+int encode_tmap_tiled(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
 
 }  // namespace umma
 }  // namespace cor

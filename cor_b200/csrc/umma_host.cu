@@ -72,5 +72,43 @@ int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return COR_OK;
 }
 
+int encode_tmap_tiled(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return COR_ECUDA;
+  if (rank < 1 || rank > 5 || ((uintptr_t)base & 15) != 0) {
+    set_error("encode_tmap_tiled: rank %d / base alignment", rank);
+    return COR_EINVAL;
+  }
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                                               : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    st[i] = strides_bytes[i];
+    if (st[i] % 16 != 0) {
+      set_error("encode_tmap_tiled: stride %d = %llu bytes is not a multiple of 16", i, (unsigned long long)st[i]);
+      return COR_EINVAL;
+    }
+  }
+  if (((uint64_t)bx[0] * elem_bytes) % 16 != 0) {
+    set_error("encode_tmap_tiled: inner box of %u x %d bytes is not a multiple of 16", bx[0], elem_bytes);
+    return COR_EINVAL;
+  }
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT && r != CUDA_ERROR_NOT_INITIALIZED) break;
+    bind_context_of(base);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (rank %d, elem %d B) failed with CUresult %d", rank, elem_bytes, (int)r);
+    return COR_ECUDA;
+  }
+  return COR_OK;
+}
+
 }  // namespace umma
 }  // namespace cor

@@ -26,7 +26,8 @@ from . import ops
 from ._lib import CorError
 
 __all__ = ["wbce_with_wiou_loss", "mask_pooling", "fg_feat_similarity_loss", "bg_feat_similarity_loss",
-           "fg_bg_feat_similarity_loss", "segmentation_loss", "region_path_loss", "BG_REFERENCE", "BG_PAIRED"]
+           "fg_bg_feat_similarity_loss", "segmentation_loss", "region_path_loss", "BG_REFERENCE", "BG_PAIRED",
+           "bce_with_iou_loss", "bce_with_dice_loss", "wbce_with_wdice_loss", "focal_loss_with_iou_loss"]
 
 BG_REFERENCE = 0   # what loss_func.py:120-123 computes (cosine over the broadcast row axis)
 BG_PAIRED = 1      # per-sample cos(bg_b, comb_b) + 1, the form its docstring describes
@@ -36,6 +37,31 @@ def wbce_with_wiou_loss(pred: torch.Tensor, mask: torch.Tensor, w1: float = 1.0,
     """utils/loss_func.py:5-32.  pred logits [N,C,H,W]; mask [N,C,H,W] in [0,1] (a mask at another
     resolution is bilinearly resampled inside the kernel, fusing trainer_v3_g.py:67)."""
     return ops.seg_loss(pred, mask, w1, w2)
+
+
+# ---- Class N: the dice / focal / plain variants whose NAMES survive in the reference's stale bytecode
+# (utils/__pycache__/loss_func.cpython-310.pyc: bce_with_iou_loss, bce_with_dice_loss, wbce_with_wdice_loss,
+# focal_loss_with_iou_loss, ...) but whose source and constants do not (SURVEY.md 0.2).  Textbook definitions, restated in
+# oracle/aten_port.py; every one is the same single pass as wbce_with_wiou_loss with another coefficient vector, forward
+# and backward.  Parity unpinned by the reference.
+def bce_with_iou_loss(pred: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """mean(bce) + soft IoU loss per sample, averaged over samples."""
+    return ops.seg_loss(pred, mask, coef=ops.seg_coef(bce=1.0, iou=1.0))
+
+
+def bce_with_dice_loss(pred: torch.Tensor, mask: torch.Tensor, smooth: float = 1.0) -> torch.Tensor:
+    """mean(bce) + soft dice loss 1 - (2 sum(pt) + smooth)/(sum(p) + sum(t) + smooth)."""
+    return ops.seg_loss(pred, mask, coef=ops.seg_coef(bce=1.0, dice=1.0), dice_smooth=smooth)
+
+
+def wbce_with_wdice_loss(pred: torch.Tensor, mask: torch.Tensor, smooth: float = 1.0) -> torch.Tensor:
+    """Edge-weighted BCE (loss_func.py:18-22) + edge-weighted dice 1 - (2 sum(ptw) + smooth)/(sum((p+t)w) + smooth)."""
+    return ops.seg_loss(pred, mask, coef=ops.seg_coef(wbce=1.0, wdice=1.0), dice_smooth=smooth)
+
+
+def focal_loss_with_iou_loss(pred: torch.Tensor, mask: torch.Tensor, alpha: float = 0.25, gamma: float = 2.0) -> torch.Tensor:
+    """Sigmoid focal loss mean(a_t (1 - p_t)^gamma bce) + soft IoU loss."""
+    return ops.seg_loss(pred, mask, coef=ops.seg_coef(focal=1.0, iou=1.0), focal_alpha=alpha, focal_gamma=gamma)
 
 
 def segmentation_loss(pred: torch.Tensor, query_mask: torch.Tensor, w1: float = 1.0, w2: float = 1.0) -> torch.Tensor:

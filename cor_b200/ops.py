@@ -17,7 +17,7 @@ from ._lib import BF16, F32, U8, W_CLAMP, W_PLAIN, W_SIGMOID, CorError, check, d
 
 __all__ = [
     "mask_prep", "region_pool", "fgbg_losses", "seg_loss", "l2_normalize", "similarity", "infonce_loss",
-    "topk_retrieve", "val_postprocess", "RegionPool", "W_PLAIN", "W_CLAMP", "W_SIGMOID",
+    "topk_retrieve", "val_postprocess", "RegionPool", "W_PLAIN", "W_CLAMP", "W_SIGMOID", "seg_coef", "clear_caches",
 ]
 
 _f = C.c_float
@@ -337,9 +337,22 @@ def fgbg_losses(fg_rows: torch.Tensor, bg_rows: Optional[torch.Tensor], comb: to
 # --------------------------------------------------------------------------------------------------
 # segmentation loss
 # --------------------------------------------------------------------------------------------------
+def seg_coef(**terms) -> tuple:
+    """Coefficient vector of the segmentation loss: seg_coef(wbce=1, wiou=1) is loss_func.py:31."""
+    names = ("wbce", "wiou", "dice", "bce", "iou", "wdice", "focal")
+    bad = set(terms) - set(names)
+    if bad:
+        raise CorError(f"seg_coef: unknown terms {sorted(bad)} (known: {names})")
+    return tuple(float(terms.get(n, 0.0)) for n in names)
+
+
+def _coef_array(coef):
+    return (C.c_float * L.SEG_NTERMS)(*coef)
+
+
 class _SegLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, mask, w1, w2, mask_scale, focal_alpha, focal_gamma, dice_smooth):
+    def forward(ctx, pred, mask, coef, mask_scale, focal_alpha, focal_gamma, dice_smooth):
         dev = require_cuda(pred, mask)
         pred_c = _as_supported_float(pred)
         if mask.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
@@ -356,38 +369,43 @@ class _SegLossFn(torch.autograd.Function):
         H, W = pred_c.shape[2:]
         lib = L.load()
         out8 = torch.empty(8, dtype=torch.float32, device=dev)
-        per = torch.empty((N, 8), dtype=torch.float32, device=dev)
+        per = torch.empty((N, lib.cor_seg_loss_npartials()), dtype=torch.float32, device=dev)
         need = pred.requires_grad
         t_save = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need else None
         w_save = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need else None
         work = _work(lib.cor_seg_loss_work_bytes(N, H, W), dev)
         _call("cor_seg_loss_fwd", dev, ptr(pred_c), dtype_code(pred_c), ptr(mask_c), dtype_code(mask_c),
-              _f(_mask_scale(mask_c, mask_scale)), N, H, W, Hm, Wm, _ll(nstride), _f(w1), _f(w2), _f(focal_alpha), _f(focal_gamma),
+              _f(_mask_scale(mask_c, mask_scale)), N, H, W, Hm, Wm, _ll(nstride), _coef_array(coef), _f(focal_alpha), _f(focal_gamma),
               _f(dice_smooth), ptr(out8), ptr(per), ptr(t_save), ptr(w_save), ptr(work))
         ctx.save_for_backward(pred_c, t_save, w_save, per)
-        ctx.cfg = (N, H, W, float(w1), float(w2), pred.dtype)
+        ctx.cfg = (N, H, W, tuple(coef), float(dice_smooth), float(focal_alpha), float(focal_gamma), pred.dtype)
         return out8[0].clone(), out8.clone()
 
     @staticmethod
     def backward(ctx, g_loss, _g_extra):
         pred_c, t_save, w_save, per = ctx.saved_tensors
-        N, H, W, w1, w2, in_dtype = ctx.cfg
+        N, H, W, coef, dice_smooth, focal_alpha, focal_gamma, in_dtype = ctx.cfg
         dev = pred_c.device
         g = g_loss.reshape(1).float().contiguous()
         g_pred = torch.empty_like(pred_c)
-        _call("cor_seg_loss_bwd", dev, ptr(pred_c), dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _f(w1), _f(w2),
-              ptr(g), ptr(g_pred), dtype_code(g_pred))
-        return g_pred.to(in_dtype), None, None, None, None, None, None, None
+        _call("cor_seg_loss_bwd", dev, ptr(pred_c), dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _coef_array(coef),
+              _f(dice_smooth), _f(focal_alpha), _f(focal_gamma), ptr(g), ptr(g_pred), dtype_code(g_pred))
+        return g_pred.to(in_dtype), None, None, None, None, None, None
 
 
 def seg_loss(pred: torch.Tensor, mask: torch.Tensor, w1: float = 1.0, w2: float = 1.0, mask_scale: Optional[float] = None,
-             focal_alpha: float = 0.25, focal_gamma: float = 2.0, dice_smooth: float = 1.0, return_extras: bool = False):
+             focal_alpha: float = 0.25, focal_gamma: float = 2.0, dice_smooth: float = 1.0, return_extras: bool = False,
+             coef: Optional[tuple] = None):
     """Weighted BCE + weighted IoU (loss_func.py:5-32); ``mask`` may be at any resolution -- it is
-    bilinearly resampled to the logit grid inside the kernel (trainer_v3_g.py:67).  With
-    ``return_extras`` also returns the 8-vector {loss, dice, focal, mean wbce, mean wiou, ...}."""
-    # the focal term (a powf per pixel) is only evaluated when the extras are asked for
-    loss, extra = _SegLossFn.apply(pred, mask, float(w1), float(w2), mask_scale, float(focal_alpha),
-                                   float(focal_gamma) if return_extras else -1.0, float(dice_smooth))
+    bilinearly resampled to the logit grid inside the kernel (trainer_v3_g.py:67).  ``coef``
+    (:func:`seg_coef`) selects another combination of the seven per-sample terms the kernel produces
+    (dice / plain bce / iou / weighted dice / focal are Class N); all of them are differentiable.
+    With ``return_extras`` also returns the 8-vector {loss, dice, focal, wbce, wiou, bce, iou, wdice}."""
+    if coef is None:
+        coef = seg_coef(wbce=w1, wiou=w2)
+    want_focal = return_extras or coef[L.SEG_FOCAL] != 0.0       # the focal term is a powf per pixel: only on request
+    loss, extra = _SegLossFn.apply(pred, mask, tuple(coef), mask_scale, float(focal_alpha),
+                                   float(focal_gamma) if want_focal else -1.0, float(dice_smooth))
     return (loss, extra) if return_extras else loss
 
 

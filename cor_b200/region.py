@@ -131,7 +131,7 @@ class _FusedStepFn(torch.autograd.Function):
         N = B
         H, W = pred_c.shape[2:]
         out8 = torch.empty(8, **f32)
-        per = torch.empty((N, 8), **f32)
+        per = torch.empty((N, lib.cor_seg_loss_npartials()), **f32)
         need_pred = pred.requires_grad
         t_save = torch.empty((N, H, W), **f32) if need_pred else None
         w_save = torch.empty((N, H, W), **f32) if need_pred else None
@@ -148,7 +148,7 @@ class _FusedStepFn(torch.autograd.Function):
                 ev_q = torch.cuda.Event()
                 ev_q.record(side)
             call("cor_seg_loss_fwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(gt), L.dtype_code(gt), _f(ops._mask_scale(gt, None)), N, H, W,
-                 Hm, Wm, _ll(gt.stride(0)), _f(1.0), _f(1.0), _f(0.25), _f(-1.0), _f(1.0), ptr(out8), ptr(per), ptr(t_save), ptr(w_save),
+                 Hm, Wm, _ll(gt.stride(0)), None, _f(0.25), _f(-1.0), _f(1.0), ptr(out8), ptr(per), ptr(t_save), ptr(w_save),
                  ptr(seg_work))
         # 1. masks -> bf16 weights (+ raw fp32 weights for the backward) + full-resolution stats
         Rp = (M + 1 + 15) // 16 * 16
@@ -271,8 +271,8 @@ class _FusedStepFn(torch.autograd.Function):
             if side is not None:
                 side.wait_stream(cur)
             with torch.cuda.stream(side if side is not None else cur):
-                call("cor_seg_loss_bwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, _f(1.0), _f(1.0),
-                     ptr(g), ptr(gp), L.dtype_code(gp))
+                call("cor_seg_loss_bwd", dev, ptr(pred_c), L.dtype_code(pred_c), ptr(t_save), ptr(w_save), ptr(per), N, H, W, None, _f(1.0),
+                     _f(0.25), _f(-1.0), ptr(g), ptr(gp), L.dtype_code(gp))
             return gp
 
         px = ctx.px

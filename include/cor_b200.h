@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define COR_ABI_VERSION 1
+#define COR_ABI_VERSION 2
 
 /* element types */
 #define COR_F32 0
@@ -149,17 +149,34 @@ int cor_step_combine(const float* seg, const float* fgbg, const float* nce, floa
 /* ------------------------------------------------------------------------------------------
  * Segmentation loss (loss_func.py:5-32) with the target resample of trainer_v3_g.py:67 fused in.
  *   pred [N, H, W] f32/bf16 logits; mask [N, Hm, Wm] f32/bf16/u8 (resampled to HxW if sizes differ)
- *   out8 [8]: {loss, dice_loss, focal_loss, 0...}; per_sample [N, 8] partial sums saved for backward;
+ *   Per sample, from ONE pass over (pred, mask), seven terms (t = target, p = sigmoid(pred),
+ *   w = 1 + 5|boxmean31(t) - t|, sm = dice_smooth):
+ *     COR_SEG_WBCE  sum(w bce)/sum(w)                               loss_func.py:21-22
+ *     COR_SEG_WIOU  1 - (sum(ptw) + 1e-6)/(sum((p+t)w) - sum(ptw) + 1e-6)   loss_func.py:25-29
+ *     COR_SEG_DICE  1 - (2 sum(pt) + sm)/(sum(p) + sum(t) + sm)     [Class N: names only in the reference's stale .pyc]
+ *     COR_SEG_BCE   mean(bce)                                       [Class N]
+ *     COR_SEG_IOU   1 - (sum(pt) + 1e-6)/(sum(p) + sum(t) - sum(pt) + 1e-6)   [Class N]
+ *     COR_SEG_WDICE 1 - (2 sum(ptw) + sm)/(sum((p+t)w) + sm)        [Class N]
+ *     COR_SEG_FOCAL mean(a_t (1 - p_t)^gamma bce)                   [Class N; evaluated only when focal_gamma >= 0]
+ *   loss = mean_n sum_k coef7[k] term_k[n]; coef7 is a HOST array of COR_SEG_NTERMS floats, NULL = {1, 1, 0, ...}
+ *   (= wbce_with_wiou_loss, loss_func.py:31).
+ *   out8 [8]: {loss, dice, focal, wbce, wiou, bce, iou, wdice}, each the mean over samples;
+ *   per_sample [N, cor_seg_loss_npartials()] partial sums saved for backward;
  *   t_save, w_save [N,H,W] f32 (resampled target, edge weight) or NULL when no backward is needed.
+ *   Kernels: a TMA-streamed row-strip kernel when the mask is at the logit size or at exactly 4x it (W <= 256,
+ *   W % 16 == 0, 16-byte aligned), a 64x64 tile kernel otherwise (COR_SEG_STRIP=0 forces the latter).
  * ---------------------------------------------------------------------------------------- */
+enum { COR_SEG_WBCE = 0, COR_SEG_WIOU = 1, COR_SEG_DICE = 2, COR_SEG_BCE = 3, COR_SEG_IOU = 4, COR_SEG_WDICE = 5, COR_SEG_FOCAL = 6,
+       COR_SEG_NTERMS = 7 };
+int cor_seg_loss_npartials(void);
 size_t cor_seg_loss_work_bytes(int N, int H, int W);
 int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* mask, int mask_dtype, float mask_scale,
-                     int N, int H, int W, int Hm, int Wm, long long mask_nstride /* elements between samples; <=0: Hm*Wm */, float w1, float w2, float focal_alpha,
-                     float focal_gamma, float dice_smooth, float* out8, float* per_sample, float* t_save,
-                     float* w_save, void* work, cor_stream_t stream);
+                     int N, int H, int W, int Hm, int Wm, long long mask_nstride /* elements between samples; <=0: Hm*Wm */,
+                     const float* coef7, float focal_alpha, float focal_gamma, float dice_smooth, float* out8,
+                     float* per_sample, float* t_save, float* w_save, void* work, cor_stream_t stream);
 int cor_seg_loss_bwd(const void* pred, int pred_dtype, const float* t_save, const float* w_save,
-                     const float* per_sample, int N, int H, int W, float w1, float w2, const float* g_loss,
-                     void* g_pred, int g_dtype, cor_stream_t stream);
+                     const float* per_sample, int N, int H, int W, const float* coef7, float dice_smooth, float focal_alpha,
+                     float focal_gamma, const float* g_loss, void* g_pred, int g_dtype, cor_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Region x query similarity and InfoNCE (Class N: no reference implementation; nearest call

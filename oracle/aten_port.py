@@ -82,6 +82,43 @@ def edge_weighted_seg_loss(pred, target, w1: float = 1.0, w2: float = 1.0) -> to
     return (w1 * wbce + w2 * wiou).mean()
 
 
+# ---- Class N segmentation-loss variants (names from the reference's stale .pyc, textbook definitions) ----
+def _soft_terms(pred, target, smooth: float = 1.0, alpha: float = 0.25, gamma: float = 2.0):
+    """Per-sample terms [N*C] of the variants below: bce, iou, dice, wbce, wdice, focal (target at pred's size)."""
+    edge = 1 + 5 * (tf.avg_pool2d(target, kernel_size=31, stride=1, padding=15) - target).abs()
+    bce = tf.binary_cross_entropy_with_logits(pred, target, reduction="none")
+    p = torch.sigmoid(pred)
+    d = (2, 3)
+    inter, sp, stt = (p * target).sum(d), p.sum(d), target.sum(d)
+    iw, uw = (p * target * edge).sum(d), ((p + target) * edge).sum(d)
+    pt = p * target + (1 - p) * (1 - target)
+    at = alpha * target + (1 - alpha) * (1 - target)
+    return {"bce": bce.mean(d), "iou": 1 - (inter + 1e-6) / (sp + stt - inter + 1e-6),
+            "dice": 1 - (2 * inter + smooth) / (sp + stt + smooth), "wbce": (edge * bce).sum(d) / edge.sum(d),
+            "wdice": 1 - (2 * iw + smooth) / (uw + smooth), "wiou": 1 - (iw + 1e-6) / (uw - iw + 1e-6),
+            "focal": (at * (1 - pt).clamp(min=0) ** gamma * bce).mean(d)}
+
+
+def bce_with_iou_loss(pred, target):
+    t = _soft_terms(pred, target)
+    return (t["bce"] + t["iou"]).mean()
+
+
+def bce_with_dice_loss(pred, target, smooth: float = 1.0):
+    t = _soft_terms(pred, target, smooth=smooth)
+    return (t["bce"] + t["dice"]).mean()
+
+
+def wbce_with_wdice_loss(pred, target, smooth: float = 1.0):
+    t = _soft_terms(pred, target, smooth=smooth)
+    return (t["wbce"] + t["wdice"]).mean()
+
+
+def focal_loss_with_iou_loss(pred, target, alpha: float = 0.25, gamma: float = 2.0):
+    t = _soft_terms(pred, target, alpha=alpha, gamma=gamma)
+    return (t["focal"] + t["iou"]).mean()
+
+
 def seg_loss_fullres(pred, query_mask) -> torch.Tensor:
     """trainer_v3_g.py:67-68."""
     return edge_weighted_seg_loss(pred, _resize(query_mask, pred.shape[2:]))

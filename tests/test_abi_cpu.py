@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(lib):
     raw = ctypes.CDLL(_lib.LIB_PATH)
     missing = [n for n in names if not hasattr(raw, n)]
     assert not missing, f"declared in include/cor_b200.h but not exported: {missing}"
-    assert lib.cor_abi_version() == 1
+    assert lib.cor_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_no_torch_types_in_the_header():
@@ -36,7 +36,9 @@ def test_no_torch_types_in_the_header():
 
 
 def test_size_queries_need_no_gpu(lib):
-    assert lib.cor_seg_loss_work_bytes(16, 256, 256) == 16 * 16 * 8 * 8
+    # max(64x64 tiles = 16, strips of >= 16 rows = 16) records of cor_seg_loss_npartials() doubles per sample
+    assert lib.cor_seg_loss_npartials() == 10
+    assert lib.cor_seg_loss_work_bytes(16, 256, 256) == 16 * 16 * 10 * 8
     assert lib.cor_fgbg_aux_floats(16, 256) == 16 * 8 + 3 * 256
     assert lib.cor_mask_prep_work_bytes(4, 64, 64, 16, 16) > 0
 
@@ -187,4 +189,4 @@ def test_header_is_plain_c_and_a_c_host_can_bind_it(lib, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert "ABI v1" in r.stdout and "-> -1" in r.stdout
+    assert "ABI v2" in r.stdout and "-> -1" in r.stdout

@@ -71,3 +71,19 @@ def test_dice_focal_textbook():
     pt = p * tt + (1 - p) * (1 - tt)
     focal = ((0.25 * tt + 0.75 * (1 - tt)) * (1 - pt) ** 2 * bce).mean()
     np.testing.assert_allclose(no.focal_loss(x, t), focal.item(), rtol=1e-5)
+
+
+def test_port_seg_variants_agree_with_numpy_restatement():
+    """The torch restatement of the Class-N segmentation variants (oracle/aten_port.py) against the numpy one."""
+    import torch
+    from cor_b200 import synth
+    from oracle import aten_port as ap
+    rng = np.random.default_rng(5)
+    t = synth.make_masks(rng, 3, 1, 48, 40, soft=True, degenerate=False)
+    x = synth.make_logits(rng, 3, 48, 40)
+    terms = ap._soft_terms(torch.from_numpy(x), torch.from_numpy(t))
+    np.testing.assert_allclose(float(terms["dice"].mean()), float(no.dice_loss(x, t)), rtol=1e-5)
+    np.testing.assert_allclose(float(terms["focal"].mean()), float(no.focal_loss(x, t)), rtol=1e-5)
+    np.testing.assert_allclose(float((terms["wbce"] + terms["wiou"]).mean()), float(no.wbce_with_wiou_loss(x, t)), rtol=1e-5)
+    np.testing.assert_allclose(float(ap.bce_with_dice_loss(torch.from_numpy(x), torch.from_numpy(t))),
+                               float(terms["bce"].mean() + terms["dice"].mean()), rtol=1e-6)
