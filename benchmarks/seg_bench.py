@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Segmentation-loss kernels alone (utils/loss_func.py:5-32 is what train_stage calls every step): CUDA-event time of
-ONE forward call (tile/strip kernel + finalize) and of forward+backward after an L2 flush, median of --iters, for the
+"""Segmentation-loss kernels alone (utils/loss_func.py:5-32 is what train_stage calls every step): the op is captured
+into a CUDA graph (so the Python wrapper's allocations and launch overhead stay out of the number: at B=16 they are
+several times the kernel) and ONE replay is timed with CUDA events after an L2 flush, median of --iters: forward
+(tile/strip kernel + finalize + the two 8-float copies of the wrapper) and forward+backward, for the
 strip kernel and for the 64x64 tile kernel (COR_SEG_STRIP=0), against the HBM peak on ALGORITHMIC bytes
 (18 B/pixel with bf16 logits and 4 fp32 taps) and on the DRAM-sector floor (rows 4y+1, 4y+2 whole: 34 B/pixel).
 
@@ -26,8 +28,18 @@ flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
 
 
 def timed(fn):
-    for _ in range(3):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
         fn()
+    fn = graph.replay
+    fn()
     ts = []
     for _ in range(args.iters):
         flush.add_(1)

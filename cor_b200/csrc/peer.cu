@@ -255,13 +255,9 @@ int cor_peer_close(void* ptr) {
 
 // COR_PEER_TIMEOUT_S: seconds a wait may last before the error word is set (default 600; 0 = unbounded)
 static unsigned long long peer_timeout_ns() {
-  static unsigned long long cached = ~0ull;
-  if (cached == ~0ull) {
-    double s = 600.0;
-    if (const char* e = getenv("COR_PEER_TIMEOUT_S")) s = atof(e);
-    cached = s <= 0.0 ? 0ull : (unsigned long long)(s * 1e9);
-  }
-  return cached;
+  double s = 600.0;                                   // read per launch: a getenv is nothing beside a kernel launch
+  if (const char* e = getenv("COR_PEER_TIMEOUT_S")) s = atof(e);
+  return s <= 0.0 ? 0ull : (unsigned long long)(s * 1e9);
 }
 
 static int peer_ctl(const char* what, void* const* peer_flags, void* state, int rank, int world, int channel, PeerCtl* c) {

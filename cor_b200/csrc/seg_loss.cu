@@ -318,7 +318,6 @@ extern "C" int cor_seg_loss_fwd(const void* pred, int pred_dtype, const void* ma
   if (mask_nstride <= 0) mask_nstride = (long long)Hm * Wm;
   COR_REQUIRE(mask_nstride >= (long long)Hm * Wm, "cor_seg_loss_fwd: mask_nstride too small");
   const SegCoef coef = make_coef(coef7);
-  if (coef.c[6] == 0.f && focal_gamma >= 0.f && coef7) focal_gamma = -1.f;     // nobody asked for the focal term: skip its powf
   int tiles = 0;
   const char* knob = getenv("COR_SEG_STRIP");                                  // A/B knob, read per call
   const bool no_strip = knob && atoi(knob) == 0;

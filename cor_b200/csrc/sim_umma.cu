@@ -36,7 +36,7 @@ constexpr int kSimABytes = kSimHalf * kSimBK * 2;  // 16 KB: one k-block of one 
 constexpr int kSimBBytes = kSimBN * kSimBK * 2;    // 16 KB: one stage of regions
 constexpr int kSimMaxKB = 4;                       // D <= 256
 #ifndef COR_SIM_POLY_OF4
-#define COR_SIM_POLY_OF4 2                         // of every 4 element pairs, how many take the FMA-pipe exp2 (0 = all MUFU)
+#define COR_SIM_POLY_OF4 0                         // of every 4 element pairs, how many take the FMA-pipe exp2 (0 = all MUFU)
 #endif
 constexpr int kSimPolyOf4 = COR_SIM_POLY_OF4;
 static_assert(kSimBN == 128, "the epilogue is unrolled for four 32-column chunks");

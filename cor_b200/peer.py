@@ -171,8 +171,8 @@ def get_exchange(n_local: int, Cc: int, device, group=None) -> Optional[PeerExch
     first use per shape."""
     if not enabled() or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
-    if dist.get_backend(group) != "nccl" and os.environ.get("COR_PEER_ANY_BACKEND", "0") != "1":
-        return None       # gloo plumbing is only for the one-GPU emulation of the peer test
+    if dist.get_backend(group) != "nccl":
+        return None
     key = (n_local, Cc, torch.device(device).index, id(group))
     px = _CACHE.get(key)
     if px is None:
