@@ -89,6 +89,8 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_sim_lse_parts", i, i, p, p, i, i, i, f, p, C.POINTER(i), C.POINTER(i), p)
         _sig(lib, "cor_infonce_tail", i, p, i, i, p, p, p, i, i, i, f, p, p, p, p, p, f, f, f, p, p)
         _sig(lib, "cor_infonce_bwd", i, p, p, p, p, i, i, i, f, p, f, p, p, p, p)
+        _sig(lib, "cor_infonce_bwd_umma_work_bytes", sz, i, i, i)
+        _sig(lib, "cor_infonce_bwd_umma", i, p, p, i, i, i, f, p, p, p, f, p, p, p, p)
         _sig(lib, "cor_topk", i, p, p, p, i, i, i, i, p, p, p)
         _sig(lib, "cor_l2_normalize", i, p, i, i, i, p, p, p, p)
         _sig(lib, "cor_val_post_work_bytes", sz, i, i, i)

@@ -17,8 +17,13 @@
 // i+1 overlap the epilogue of tile i.  With few queries the kernel is HBM-bound on the region stream;
 // with hundreds of queries it is tensor-pipe-bound.
 //
-// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM owner + MMA issuer, 2..9 = epilogue
-// (warp w reads TMEM lane quarter w % 4 of half (w - 2) / 4).
+// Warp roles (320 threads): 0..7 = epilogue (warp w reads TMEM lane quarter w % 4 of half w / 4), 8 = TMA producer,
+// 9 = TMEM owner + MMA issuer.  The two single-thread roles sit at the HIGHEST warp ids on purpose: the SM's issue
+// arbiter favours high warp ids, and a producer / MMA thread that has to queue behind two busy epilogue warps of its
+// sub-partition starves the tensor pipe (measured: the kernel's time grew linearly with the epilogue's instruction
+// count while the tensor pipe sat at 40 %).  The producer also prefetches region tiles into L2 a few tiles ahead, so
+// the stage loads are L2 hits: with D = 256 only six 16-KB stages fit beside the resident queries, i.e. ~2 stages in
+// flight, which covers an L2 hit's latency but not a DRAM miss's.
 #include <stdlib.h>
 
 #include "umma.cuh"
@@ -39,6 +44,11 @@ constexpr int kSimMaxKB = 4;                       // D <= 256
 #define COR_SIM_POLY_OF4 0                         // of every 4 element pairs, how many take the FMA-pipe exp2 (0 = all MUFU)
 #endif
 constexpr int kSimPolyOf4 = COR_SIM_POLY_OF4;
+constexpr int kSimTmaWarp = 8, kSimMmaWarp = 9;    // epilogue = warps 0..7
+#ifndef COR_SIM_PREFETCH
+#define COR_SIM_PREFETCH 3
+#endif
+constexpr int kSimPrefetch = COR_SIM_PREFETCH;     // region tiles prefetched into L2 ahead of the stage loads (0 = off)
 static_assert(kSimBN == 128, "the epilogue is unrolled for four 32-column chunks");
 
 struct SimSmemTail {
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
     for (int i = 0; i < 2; ++i) { mbar_init(&tail->acc_full[i], 1); mbar_init(&tail->acc_empty[i], 8); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tail->tmem_base, 512);
+  if (warp == kSimMmaWarp) tmem_alloc(&tail->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   if (cl > 1) cluster_sync();       // every CTA's barriers are initialised before any peer multicasts into them
@@ -91,14 +101,20 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
   const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
   const int slice_rows = kSimBN / cl;
 
-  if (warp == 0) {
+  if (warp == kSimTmaWarp) {
     if (lane == 0) {
       mbar_expect_tx(&tail->qfull, (uint32_t)(nhalf * nkb * kSimABytes));
       for (int hf = 0; hf < nhalf; ++hf)
         for (int kb = 0; kb < nkb; ++kb)
           tma_load_2d(q_smem + (hf * nkb + kb) * kSimABytes, &tmQ, &tail->qfull, kb * kSimBK, q0 + hf * kSimHalf, kEvictLast);
       int it = 0;
+      for (int t = blockIdx.x; t < ntiles && t < (int)blockIdx.x + kSimPrefetch * (int)gridDim.x; t += gridDim.x)
+        if (crank == 0)
+          for (int kb = 0; kb < nkb; ++kb) tma_prefetch_2d(&tmR, kb * kSimBK, t * kSimBN);
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tp = t + kSimPrefetch * (int)gridDim.x;          // keep kSimPrefetch tiles of this CTA on their way into L2
+        if (kSimPrefetch > 0 && tp < ntiles && crank == 0)
+          for (int kb = 0; kb < nkb; ++kb) tma_prefetch_2d(&tmR, kb * kSimBK, tp * kSimBN);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int st = it % nstages;
           mbar_wait(&tail->empty[st], ((it / nstages) & 1) ^ 1);
@@ -111,7 +127,7 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kSimMmaWarp) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kSimHalf, kSimBN);
       mbar_wait(&tail->qfull, 0);
@@ -138,7 +154,7 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
       }
     }
   } else {
-    const int e = warp - 2;
+    const int e = warp;
     const int qd = warp & 3;                       // TMEM lane quarter this warp may read
     const int hf = e >> 2;                         // query half (accumulator) this warp drains
     const int q = q0 + hf * kSimHalf + qd * 32 + lane;
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (cl > 1) cluster_sync();       // no CTA leaves while a peer may still multicast into it or arrive on its barriers
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == kSimMmaWarp) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace cor

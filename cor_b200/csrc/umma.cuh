@@ -60,6 +60,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// L2 prefetch of a 2-D tile (no shared memory involved): issued a few tiles ahead of the stage loads so that those hit L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
+}
+
 // 3-D / 4-D tiled loads (no swizzle): the segmentation-loss strip kernel streams mask-row bands and logit rows with these.
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, uint64_t hint) {
   asm volatile(

@@ -30,7 +30,7 @@ _KERNELS_PER_CALL = {
     "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 1, "cor_rows_finalize": 1,
     "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_umma": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
     "cor_fgbg_loss_bwd": 1, "cor_step_combine": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
-    "cor_sim_umma_fwd": 2, "cor_infonce_coef": 1, "cor_sim_umma_coef": 1, "cor_sim_lse_parts": 1, "cor_infonce_tail": 1, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
+    "cor_sim_umma_fwd": 2, "cor_infonce_coef": 1, "cor_sim_umma_coef": 1, "cor_infonce_bwd_umma": 3, "cor_sim_lse_parts": 1, "cor_infonce_tail": 1, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
     "cor_val_post": 3, "cor_soft_metrics": 2,
 }
 
@@ -534,17 +534,14 @@ class _InfoNCEFn(torch.autograd.Function):
         lib = L.load()
         gl = g.reshape(1).float().contiguous()
         if _infonce_bwd_dense(Nq, Nr, D, ctx.engine):
-            # hundreds of queries: our tensor-core similarity GEMM with the coefficient epilogue (P in bf16, S never
-            # written), then two plain library GEMMs with fp32 output (dQ = P R, dR = P^T Q)
-            P = torch.empty((Nq, Nr), dtype=torch.bfloat16, device=dev)
-            if os.environ.get("COR_NCE_COEF", "fused") == "fused":
-                _call("cor_sim_umma_coef", dev, ptr(r16), ptr(q16), Nr, Nq, D, _f(inv_tau), ptr(lse), ptr(tg), ptr(gl), _f(1.0), ptr(P))
-            else:                              # two-pass variant (A/B): S in fp32, then the coefficient kernel
-                S, _ = _sim_forward(r16, q16, 1.0, True, False, "umma")
-                _call("cor_infonce_coef", dev, ptr(S), ptr(lse), ptr(tg), Nq, Nr, _f(inv_tau), ptr(gl), _f(1.0), ptr(P))
-                del S
-            gq = torch.mm(P, r16, out_dtype=torch.float32) if q_need else None
-            gr = torch.mm(P.t(), q16, out_dtype=torch.float32) if r_need else None
+            # hundreds of queries: both products on our tensor-core kernel (csrc/nce_bwd_umma.cu) -- the S tile is
+            # recomputed, turned into bf16 coefficients in registers and fed straight back as an MMA operand; no S, no P,
+            # no library GEMM
+            gq = torch.empty((Nq, D), dtype=torch.float32, device=dev) if q_need else None
+            gr = torch.empty((Nr, D), dtype=torch.float32, device=dev) if r_need else None
+            work = _work(lib.cor_infonce_bwd_umma_work_bytes(Nq, Nr, D), dev)
+            _call("cor_infonce_bwd_umma", dev, ptr(r16), ptr(q16), Nr, Nq, D, _f(inv_tau), ptr(lse), ptr(tg), ptr(gl), _f(1.0), ptr(gr),
+                  ptr(gq), ptr(work))
         else:
             gr = torch.empty((Nr, D), dtype=torch.float32, device=dev)
             gq = torch.empty((Nq, D), dtype=torch.float32, device=dev)

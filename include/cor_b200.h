@@ -219,6 +219,15 @@ int cor_infonce_fwd(const void* regions, const void* queries, const long long* t
 int cor_infonce_bwd(const void* regions, const void* queries, const long long* targets, const float* lse,
                     int Nr, int Nq, int D, float inv_tau, const float* g_loss, float g_mul, float* g_regions,
                     float* g_queries, void* work, cor_stream_t stream);
+/* InfoNCE backward for MANY queries on tcgen05 tensor cores (csrc/nce_bwd_umma.cu): dQ = P R and dR = P^T Q with
+ * P = (exp(S/tau - lse) - onehot(target)) * g_loss[0] * g_mul / (tau * Nq) formed tile by tile in registers and fed back
+ * to the tensor cores through shared memory -- neither S nor P is ever written to global memory and no library GEMM
+ * is involved.  regions [Nr,D], queries [Nq,D] bf16, D in {64,128,192,256}; g_regions [Nr,D] / g_queries [Nq,D] f32
+ * (either may be NULL); work: cor_infonce_bwd_umma_work_bytes() bytes (fp32 split partials, folded in fixed order). */
+size_t cor_infonce_bwd_umma_work_bytes(int Nq, int Nr, int D);
+int cor_infonce_bwd_umma(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, const float* lse,
+                         const long long* targets, const float* g_loss, float g_mul, float* g_regions, float* g_queries,
+                         void* work, cor_stream_t stream);
 
 /* Top-k retrieval: per query the k best regions under (score desc, index asc), where score is the
  * canonical value fl32(sum in fp64 of exact bf16 products).  S is the (tensor-core) prefilter

@@ -246,10 +246,12 @@ def test_full_size_config2_tensor_core_step_vs_exact_engines():
     assert torch.equal(ia, ib)
 
 
-@pytest.mark.parametrize("shape", [(4096, 256, 256), (5001, 130, 128)])
+@pytest.mark.parametrize("shape", [(4096, 256, 256), (5001, 130, 128), (1000, 300, 192), (4100, 128, 64), (9000, 129, 256)])
 def test_infonce_dense_backward_vs_streaming_and_oracle(shape):
-    """Many-query InfoNCE backward (tensor-core S, bf16 coefficient matrix, two library GEMMs) against the exact
-    streaming backward and the ATen port.  bf16 coefficients: gradients agree to a few 1e-3 of their norm."""
+    """Many-query InfoNCE backward on the tcgen05 kernel of csrc/nce_bwd_umma.cu (S tile recomputed, bf16 coefficients
+    formed in registers and fed back through shared memory as the A operand, the region / query tile reused as an
+    MN-major B operand; no S, no P, no library GEMM) against the exact streaming backward and the ATen port.
+    bf16 coefficients: gradients agree to a few 1e-3 of their norm.  Ragged tiles in both dimensions, all four D."""
     from cor_b200 import ops, synth
     from oracle import aten_port as ap
     Nr, Nq, D = shape
