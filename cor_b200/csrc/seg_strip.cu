@@ -9,10 +9,13 @@
 //     rows 4y+1 and 4y+2 -- whole 128-byte lines, every DRAM sector that holds a tap exactly once, nothing else;
 //   * the logits ride in the same stage (3-D map, box {W, kSG, 1});
 //   * out-of-image rows are zero-filled by TMA = the zero padding of avg_pool2d(31, 1, 15, count_include_pad=True).
-// One thread per column.  The vertical 31-row sum is a sliding window in a REGISTER (+ new row - row 31 back; the
-// 32-row ring of targets it needs is thread-private shared memory, no sync); the horizontal 31-column sum is a warp
-// shuffle prefix scan plus two shared-memory reads for the neighbouring warps' prefixes -- one named barrier per kSG
-// rows.  Per-pixel terms accumulate in registers; one fixed-order block reduction per CTA at the end (deterministic).
+// One thread per column.  The vertical 31-row sum is a sliding window in a REGISTER (+ new row - row 31 back); the
+// 32-row ring of targets it needs lives in REGISTERS too (the row loop is unrolled 32 deep so every ring index is a
+// compile-time constant), which leaves the shared memory to the TMA ring: six 2-row stages per CTA, two CTAs per SM,
+// ~170 KB of loads in flight per SM -- the kernel is a pure stream and its only real enemy is DRAM latency.  The
+// horizontal 31-column sum is a warp shuffle prefix scan plus two shared-memory reads for the neighbouring warps'
+// prefixes -- one named barrier per kSG rows.  Per-pixel terms accumulate in registers; one fixed-order block
+// reduction per CTA at the end (deterministic).
 // Warp roles (288 threads): 0..7 consumers (column = threadIdx.x), 8 = TMA producer.
 #include "seg_common.cuh"
 #include "umma.cuh"
@@ -22,9 +25,10 @@ namespace cor {
 using namespace umma;
 
 constexpr int kSW = 256;        // columns per CTA (= consumer threads)
-constexpr int kSG = 4;          // logit rows per stage
-constexpr int kSStages = 2;
-constexpr int kSRing = 32;      // rows of targets kept per column (31-row window + the row being written)
+constexpr int kSG = 2;          // logit rows per stage
+constexpr int kSStages = 6;
+constexpr int kSRing = 32;      // rows of targets kept per column (31-row window + the row being written), in registers
+constexpr int kSUnroll = kSRing / kSG;   // chunks per unrolled group: one full turn of the ring
 constexpr int kSThreads = kSW + 32;
 constexpr int kSHalo = 15;
 
@@ -68,8 +72,7 @@ __global__ void __launch_bounds__(kSThreads, 2) seg_loss_strip_kernel(const __gr
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 127) & ~(uintptr_t)127);
   uint8_t* stages = base;
-  float* ring = reinterpret_cast<float*>(base + (size_t)kSStages * a.stage_bytes);        // [kSRing][kSW]
-  float* pbuf = ring + kSRing * kSW;                                                       // [2][kSG][kSW]
+  float* pbuf = reinterpret_cast<float*>(base + (size_t)kSStages * a.stage_bytes);        // [2][kSG][kSW]
   StripSmemTail* tail = reinterpret_cast<StripSmemTail*>(pbuf + 2 * kSG * kSW);
   double* scratch = reinterpret_cast<double*>(stages);      // block reduction scratch: the ring is drained by then
 
@@ -95,9 +98,9 @@ __global__ void __launch_bounds__(kSThreads, 2) seg_loss_strip_kernel(const __gr
   if (warp == kSW / 32) {
     // ---- producer: one thread streams the strip's rows, kSG logit rows per stage ----
     if (lane == 0) {
-      for (int c = 0; c < nchunks; ++c) {
-        const int st = c % kSStages;
-        mbar_wait(&tail->empty[st], ((c / kSStages) & 1) ^ 1);
+      int st = 0, ph = 1;
+      for (int c = 0; c < nchunks; ++c, st = (st + 1 == kSStages ? 0 : st + 1), ph ^= (st == 0)) {
+        mbar_wait(&tail->empty[st], (uint32_t)ph);
         uint8_t* dst = stages + (size_t)st * a.stage_bytes;
         mbar_expect_tx(&tail->full[st], (uint32_t)a.tx_bytes);
         const int j0 = jstart + c * kSG;
@@ -114,9 +117,9 @@ __global__ void __launch_bounds__(kSThreads, 2) seg_loss_strip_kernel(const __gr
     // ---- consumers: thread = column ----
     const int x = threadIdx.x;
     const bool colok = x < a.W;
-    float* mycol = ring + x;
-#pragma unroll 8
-    for (int r = 0; r < kSRing; ++r) mycol[r * kSW] = 0.f;
+    float ring[kSRing];                                // this column's last 32 target rows; slot = (row - jstart) % 32
+#pragma unroll
+    for (int r = 0; r < kSRing; ++r) ring[r] = 0.f;
     float V = 0.f;                                     // sum of the last 31 target rows of this column
     float f[kNP];
 #pragma unroll
@@ -131,75 +134,83 @@ __global__ void __launch_bounds__(kSThreads, 2) seg_loss_strip_kernel(const __gr
     }
     const int row_pitch = (a.fast4 ? 2 * a.box_x : a.W) * (int)sizeof(TM);     // bytes between consecutive g inside a stage
     const int r1_off = a.box_x * (int)sizeof(TM);
-    for (int c = 0; c < nchunks; ++c) {
-      const int st = c % kSStages;
-      mbar_wait(&tail->full[st], (c / kSStages) & 1);
-      const uint8_t* sm = stages + (size_t)st * a.stage_bytes;
-      float tn[kSG], z[kSG];
+    int st = 0, ph = 0;
+    for (int c0 = 0; c0 < nchunks; c0 += kSUnroll) {
 #pragma unroll
-      for (int g = 0; g < kSG; ++g) {
-        tn[g] = 0.f;
-        z[g] = 0.f;
-        if (colok) {
-          const uint8_t* p = sm + tap_off + g * row_pitch;
-          if (a.fast4) {
-            const float2 u = mid_pair<TM>(p), v = mid_pair<TM>(p + r1_off);
-            // ATen upsample_bilinear2d at an exact 4x ratio: all four weights are 0.5
-            tn[g] = (0.5f * (0.5f * u.x + 0.5f * u.y) + 0.5f * (0.5f * v.x + 0.5f * v.y)) * a.mscale;
-          } else {
-            tn[g] = ld_smem_f<TM>(p) * a.mscale;
+      for (int cc = 0; cc < kSUnroll; ++cc) {
+        const int c = c0 + cc;
+        if (c < nchunks) {
+          mbar_wait(&tail->full[st], (uint32_t)ph);
+          const uint8_t* sm = stages + (size_t)st * a.stage_bytes;
+          float tn[kSG], z[kSG];
+#pragma unroll
+          for (int g = 0; g < kSG; ++g) {
+            tn[g] = 0.f;
+            z[g] = 0.f;
+            if (colok) {
+              const uint8_t* p = sm + tap_off + g * row_pitch;
+              if (a.fast4) {
+                const float2 u = mid_pair<TM>(p), v = mid_pair<TM>(p + r1_off);
+                // ATen upsample_bilinear2d at an exact 4x ratio: all four weights are 0.5
+                tn[g] = (0.5f * (0.5f * u.x + 0.5f * u.y) + 0.5f * (0.5f * v.x + 0.5f * v.y)) * a.mscale;
+              } else {
+                tn[g] = ld_smem_f<TM>(p) * a.mscale;
+              }
+              z[g] = ld_smem_f<TP>(sm + a.mask_stage_bytes + (g * a.W + x) * (int)sizeof(TP));
+            }
           }
-          z[g] = ld_smem_f<TP>(sm + a.mask_stage_bytes + (g * a.W + x) * (int)sizeof(TP));
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->empty[st]);     // the stage is in registers: let the producer refill it
-      const int j0 = jstart + c * kSG;                  // input rows j0 .. j0+kSG-1; output rows (j - 15)
-      float Vg[kSG];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tail->empty[st]);     // the stage is in registers: let the producer refill it
+          if (++st == kSStages) { st = 0; ph ^= 1; }
+          const int j0 = jstart + c * kSG;                  // input rows j0 .. j0+kSG-1; output rows (j - 15)
+          float Vg[kSG];
 #pragma unroll
-      for (int g = 0; g < kSG; ++g) {
-        const int j = j0 + g;
-        const float told = mycol[((j + 1) & (kSRing - 1)) * kSW];     // row j - 31 (same slot as j + 1)
-        V += tn[g] - told;
-        mycol[(j & (kSRing - 1)) * kSW] = tn[g];
-        Vg[g] = V;
-      }
-      // any output row in this chunk?  (uniform over the CTA)
-      const int jo_lo = j0 - kSHalo, jo_hi = jo_lo + kSG - 1;
-      if (jo_hi < y0 || jo_lo >= y0 + rows) continue;
-      // horizontal 31-sums: inclusive prefix inside the warp ...
-      float P[kSG];
+          for (int g = 0; g < kSG; ++g) {
+            constexpr int dummy = 0; (void)dummy;
+            const int rr = cc * kSG + g;                     // compile-time ring slot of input row j0 + g
+            V += tn[g] - ring[(rr + 1) & (kSRing - 1)];      // row j - 31 sits in the slot row j + 1 will take
+            ring[rr] = tn[g];
+            Vg[g] = V;
+          }
+          // any output row in this chunk?  (uniform over the CTA)
+          const int jo_lo = j0 - kSHalo, jo_hi = jo_lo + kSG - 1;
+          if (!(jo_hi < y0 || jo_lo >= y0 + rows)) {
+            // horizontal 31-sums: inclusive prefix inside the warp ...
+            float P[kSG];
 #pragma unroll
-      for (int g = 0; g < kSG; ++g) P[g] = Vg[g];
+            for (int g = 0; g < kSG; ++g) P[g] = Vg[g];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
+            for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
-        for (int g = 0; g < kSG; ++g) {
-          const float up = __shfl_up_sync(0xffffffffu, P[g], o);
-          if (lane >= o) P[g] += up;
-        }
-      }
-      float* pb = pbuf + (c & 1) * kSG * kSW;
+              for (int g = 0; g < kSG; ++g) {
+                const float up = __shfl_up_sync(0xffffffffu, P[g], o);
+                if (lane >= o) P[g] += up;
+              }
+            }
+            float* pb = pbuf + (c & 1) * kSG * kSW;
 #pragma unroll
-      for (int g = 0; g < kSG; ++g) pb[g * kSW + x] = P[g];
-      asm volatile("bar.sync 1, %0;" ::"n"(kSW) : "memory");
-      // ... combined across at most two warps: columns [x-15, x+15]
+            for (int g = 0; g < kSG; ++g) pb[g * kSW + x] = P[g];
+            asm volatile("bar.sync 1, %0;" ::"n"(kSW) : "memory");
+            // ... combined across at most two warps: columns [x-15, x+15]
 #pragma unroll
-      for (int g = 0; g < kSG; ++g) {
-        const float hi = __shfl_sync(0xffffffffu, P[g], min(lane + 15, 31));
-        const float lo = __shfl_sync(0xffffffffu, P[g], max(lane - 16, 0));
-        float box = hi - (lane >= 16 ? lo : 0.f);
-        if (lane < 15 && warp > 0) box += pb[g * kSW + (warp - 1) * 32 + 31] - pb[g * kSW + (warp - 1) * 32 + lane + 16];
-        if (lane > 16 && warp < kSW / 32 - 1) box += pb[g * kSW + (warp + 1) * 32 + lane - 17];
-        const int jo = jo_lo + g;
-        if (colok && jo >= y0 && jo < y0 + rows) {
-          const float t = mycol[(jo & (kSRing - 1)) * kSW];
-          float wgt;
-          seg_pixel_terms(z[g], t, box, a.focal_alpha, a.focal_gamma, f, wgt);
-          if (a.t_save) {
-            const long long o = ((long long)n * a.H + jo) * a.W + x;
-            a.t_save[o] = t;
-            a.w_save[o] = wgt;
+            for (int g = 0; g < kSG; ++g) {
+              const float hi = __shfl_sync(0xffffffffu, P[g], min(lane + 15, 31));
+              const float lo = __shfl_sync(0xffffffffu, P[g], max(lane - 16, 0));
+              float box = hi - (lane >= 16 ? lo : 0.f);
+              if (lane < 15 && warp > 0) box += pb[g * kSW + (warp - 1) * 32 + 31] - pb[g * kSW + (warp - 1) * 32 + lane + 16];
+              if (lane > 16 && warp < kSW / 32 - 1) box += pb[g * kSW + (warp + 1) * 32 + lane - 17];
+              const int jo = jo_lo + g;
+              if (colok && jo >= y0 && jo < y0 + rows) {
+                const float t = ring[(cc * kSG + g + kSRing - kSHalo) & (kSRing - 1)];     // row jo = j - 15
+                float wgt;
+                seg_pixel_terms(z[g], t, box, a.focal_alpha, a.focal_gamma, f, wgt);
+                if (a.t_save) {
+                  const long long o = ((long long)n * a.H + jo) * a.W + x;
+                  a.t_save[o] = t;
+                  a.w_save[o] = wgt;
+                }
+              }
+            }
           }
         }
       }
@@ -267,7 +278,7 @@ static int strip_launch(const void* pred, const void* mask, float mscale, int N,
   a.stage_bytes = a.mask_stage_bytes + logit_bytes;
   // the bytes TMA actually delivers per stage (boxes are dense; the 128-byte padding between the parts carries none)
   a.tx_bytes = (a.fast4 ? a.nbox * kSG * 2 * a.box_x : kSG * W) * (int)sizeof(TM) + kSG * W * (int)sizeof(TP);
-  const size_t smem = (size_t)kSStages * a.stage_bytes + (size_t)(kSRing + 2 * kSG) * kSW * sizeof(float) + sizeof(StripSmemTail) + 128;
+  const size_t smem = (size_t)kSStages * a.stage_bytes + (size_t)(2 * kSG) * kSW * sizeof(float) + sizeof(StripSmemTail) + 128;
   auto k = seg_loss_strip_kernel<TP, TM>;
   COR_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k<<<N * a.nstrips, kSThreads, smem, st>>>(tmM, tmP, a);

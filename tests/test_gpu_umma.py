@@ -246,7 +246,7 @@ def test_full_size_config2_tensor_core_step_vs_exact_engines():
     assert torch.equal(ia, ib)
 
 
-@pytest.mark.parametrize("shape", [(4096, 256, 256), (5001, 130, 128), (1000, 300, 192), (4100, 128, 64), (9000, 129, 256)])
+@pytest.mark.parametrize("shape", [(4096, 256, 256), (5001, 130, 128), (3000, 300, 192), (4100, 128, 64), (9000, 129, 256)])
 def test_infonce_dense_backward_vs_streaming_and_oracle(shape):
     """Many-query InfoNCE backward on the tcgen05 kernel of csrc/nce_bwd_umma.cu (S tile recomputed, bf16 coefficients
     formed in registers and fed back through shared memory as the A operand, the region / query tile reused as an
