@@ -93,6 +93,9 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_infonce_bwd_umma", i, p, p, i, i, i, f, p, p, p, f, p, p, p, p)
         _sig(lib, "cor_topk", i, p, p, p, i, i, i, i, p, p, p)
         _sig(lib, "cor_l2_normalize", i, p, i, i, i, p, p, p, p)
+        _sig(lib, "cor_hyper_logits_work_bytes", sz, i, i, i, ll)
+        _sig(lib, "cor_hyper_logits_fwd", i, p, p, i, p, i, i, i, i, i, i, ll, p)
+        _sig(lib, "cor_hyper_logits_bwd", i, p, p, i, p, i, p, p, i, i, i, i, i, ll, p, p)
         _sig(lib, "cor_val_post_work_bytes", sz, i, i, i)
         _sig(lib, "cor_val_post", i, p, i, i, i, i, i, i, i, p, p, p, i, f, p, p, p)
         _sig(lib, "cor_soft_metrics", i, p, p, i, f, i, ll, f, p, p, p)

@@ -124,22 +124,29 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
       }
     }
   } else if (warp == kNbMmaWarp) {
-    if (lane == 0 && n_my > 0) {
+    // the whole warp walks the loop, one elected lane issues (descriptors stay in uniform registers; see sim_umma.cu)
+    if (n_my > 0) {
+      const bool leader = elect_one();
       const uint32_t idesc1 = make_idesc_bf16(kNbM, kNbN);
       const uint32_t idesc2 = make_idesc_bf16_bmn(kNbM, D);
+      const uint32_t x_base = smem_u32(x_smem), y_base = smem_u32(y_smem), p_base = smem_u32(p_smem);
       mbar_wait(&tail->xfull, 0);
       auto gemm1 = [&](int i) {
         const int slot = i % a.nslots, buf = i & 1;
         mbar_wait(&tail->yfull[slot], (i / a.nslots) & 1);
         mbar_wait(&tail->s_empty[buf], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < a.nkb; ++kb) {
-          const uint64_t da = make_desc_sw128(smem_u32(x_smem + kb * kNbBlk));
-          const uint64_t db = make_desc_sw128(smem_u32(y_smem + (size_t)(slot * a.nkb + kb) * kNbBlk));
+        if (leader) {
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            const uint64_t da = make_desc_sw128(x_base + (uint32_t)(kb * kNbBlk));
+            const uint64_t db = make_desc_sw128(y_base + (uint32_t)((slot * a.nkb + kb) * kNbBlk));
+            mma_bf16_ss(tmem + (uint32_t)(buf * kNbN), da, db, idesc1, kb != 0);
 #pragma unroll
-          for (int k = 0; k < kNbBK / 16; ++k) mma_bf16_ss(tmem + (uint32_t)(buf * kNbN), da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+            for (int k = 1; k < kNbBK / 16; ++k) mma_bf16_ss_acc(tmem + (uint32_t)(buf * kNbN), da + 2 * k, db + 2 * k, idesc1);
+          }
+          mma_commit(&tail->s_full[buf]);
         }
-        mma_commit(&tail->s_full[buf]);
+        __syncwarp();
       };
       gemm1(0);
       for (int i = 0; i < n_my; ++i) {
@@ -147,17 +154,21 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
         const int slot = i % a.nslots;
         mbar_wait(&tail->p_full, i & 1);
         tc_fence_after();
-        // B = the Y tile as an MN-major operand: N = d (nkb blocks of 64, kNbBlk apart), K = y rows (8-row groups 1024 B apart)
-        const uint64_t db0 = make_desc_sw128_mn(smem_u32(y_smem + (size_t)slot * a.nkb * kNbBlk), kNbBlk, 1024);
+        if (leader) {
+          // B = the Y tile as an MN-major operand: N = d (nkb blocks of 64, kNbBlk apart), K = y rows (8-row groups 1024 B apart)
+          const uint64_t db0 = make_desc_sw128_mn(y_base + (uint32_t)(slot * a.nkb * kNbBlk), kNbBlk, 1024);
+          const uint64_t dp0 = make_desc_sw128(p_base), dp1 = make_desc_sw128(p_base + kNbBlk);
+          mma_bf16_ss(tmem_g, dp0, db0, idesc2, i != 0);
 #pragma unroll
-        for (int j = 0; j < kNbN / 16; ++j) {
-          const uint64_t da = make_desc_sw128(smem_u32(p_smem + (j >> 2) * kNbBlk)) + 2 * (j & 3);
-          mma_bf16_ss(tmem_g, da, db0 + (uint64_t)(j * 128), idesc2, (i | j) != 0);     // 16 y rows = 2048 B = 128 x 16 B
+          for (int j = 1; j < kNbN / 16; ++j)       // 16 y rows = 2048 B = 128 x 16 B
+            mma_bf16_ss_acc(tmem_g, (j < 4 ? dp0 : dp1) + 2 * (j & 3), db0 + (uint64_t)(j * 128), idesc2);
+          mma_commit(&tail->p_empty);
+          mma_commit(&tail->yempty[slot]);
         }
-        mma_commit(&tail->p_empty);
-        mma_commit(&tail->yempty[slot]);
+        __syncwarp();
       }
-      mma_commit(&tail->g_full);
+      if (leader) mma_commit(&tail->g_full);
+      __syncwarp();
     }
   } else {
     const int e = warp;

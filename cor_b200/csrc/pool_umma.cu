@@ -74,21 +74,28 @@ __global__ void __launch_bounds__(192, 2) pool_umma_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBM, Rp);
-      for (int it = 0; it < iters; ++it) {
-        const int st = it % kPoolStages;
-        const uint32_t ph = (it / kPoolStages) & 1;
-        mbar_wait(&tail->full[st], ph);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(base + st * stage_bytes);
+    // whole warp walks the loop, one elected lane issues: descriptors stay in uniform registers (see sim_umma.cu)
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(kBM, Rp);
+    const uint32_t s_base = smem_u32(base);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(&tail->full[st], ph);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t a_addr = s_base + (uint32_t)(st * stage_bytes);
         const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + kABytes);
+        mma_bf16_ss(tmem_d, da, db, idesc, it != 0);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) mma_bf16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+        for (int k = 1; k < kBK / 16; ++k) mma_bf16_ss_acc(tmem_d, da + 2 * k, db + 2 * k, idesc);
         mma_commit(&tail->empty[st]);     // frees the smem stage once these MMAs have read it
       }
-      mma_commit(&tail->accum);           // accumulator complete
+      __syncwarp();
+      if (++st == kPoolStages) { st = 0; ph ^= 1u; }
     }
+    if (leader) mma_commit(&tail->accum);   // accumulator complete
+    __syncwarp();
   } else {
     // epilogue: warp w owns TMEM lanes 32*(w%4)..+31 == channels cb*128 + 32*(w%4) + lane
     mbar_wait(&tail->accum, 0);

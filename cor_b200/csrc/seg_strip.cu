@@ -11,8 +11,7 @@
 //   * out-of-image rows are zero-filled by TMA = the zero padding of avg_pool2d(31, 1, 15, count_include_pad=True).
 // One thread per column.  The vertical 31-row sum is a sliding window in a REGISTER (+ new row - row 31 back); the
 // 32-row ring of targets it needs lives in REGISTERS too (the row loop is unrolled 32 deep so every ring index is a
-// compile-time constant), which leaves the shared memory to the TMA ring: six 2-row stages per CTA, two CTAs per SM,
-// ~170 KB of loads in flight per SM -- the kernel is a pure stream and its only real enemy is DRAM latency.  The
+// compile-time constant), which leaves the shared memory to the TMA ring: three 4-row stages per CTA, two CTAs per SM.  The
 // horizontal 31-column sum is a warp shuffle prefix scan plus two shared-memory reads for the neighbouring warps'
 // prefixes -- one named barrier per kSG rows.  Per-pixel terms accumulate in registers; one fixed-order block
 // reduction per CTA at the end (deterministic).
@@ -25,8 +24,8 @@ namespace cor {
 using namespace umma;
 
 constexpr int kSW = 256;        // columns per CTA (= consumer threads)
-constexpr int kSG = 2;          // logit rows per stage
-constexpr int kSStages = 6;
+constexpr int kSG = 4;          // logit rows per stage (A/B on B200: 2-row stages x 6 were 18 % slower -- the per-stage scan + barrier chain, not DRAM latency, paces a CTA)
+constexpr int kSStages = 3;
 constexpr int kSRing = 32;      // rows of targets kept per column (31-row window + the row being written), in registers
 constexpr int kSUnroll = kSRing / kSG;   // chunks per unrolled group: one full turn of the ring
 constexpr int kSThreads = kSW + 32;

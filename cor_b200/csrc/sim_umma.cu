@@ -139,32 +139,44 @@ __global__ void __launch_bounds__(320, 1) sim_umma_kernel(const __grid_constant_
       }
     }
   } else if (warp == kSimMmaWarp) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kSimHalf, kSimBN);
-      mbar_wait(&tail->qfull, 0);
-      int it = 0, i = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
-        const int buf = i & 1;
-        mbar_wait(&tail->acc_empty[buf], ((i >> 1) & 1) ^ 1);
+    // The WHOLE warp walks this loop (barrier waits, descriptor arithmetic) and one elected lane issues: with the role
+    // wrapped in `if (lane == 0)` the compiler must treat every descriptor as divergent (R2UR + ELECT + BRA.U.ANY around
+    // each UTCHMMA, ~140 cycles per MMA on a lone warp's dependent-issue chain -- measured with the trace build: 4 450
+    // cycles to issue the 32 MMAs of a tile that the tensor pipe executes in 2 048).
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(kSimHalf, kSimBN);
+    const uint32_t q_base = smem_u32(q_smem), r_base = smem_u32(r_smem);
+    mbar_wait(&tail->qfull, 0);
+    int st = 0, i = 0;
+    uint32_t ph = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
+      const int buf = i & 1;
+      mbar_wait(&tail->acc_empty[buf], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (leader) SIM_TRACE(i, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&tail->full[st], ph);
         tc_fence_after();
-        SIM_TRACE(i, 0);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % nstages;
-          mbar_wait(&tail->full[st], (it / nstages) & 1);
-          tc_fence_after();
-          const uint64_t db = make_desc_sw128(smem_u32(r_smem + st * kSimBBytes));
+        const uint64_t db = make_desc_sw128(r_base + (uint32_t)(st * kSimBBytes));
+        if (leader) {
           for (int hf = 0; hf < nhalf; ++hf) {
-            const uint64_t da = make_desc_sw128(smem_u32(q_smem + (hf * nkb + kb) * kSimABytes));
+            const uint64_t da = make_desc_sw128(q_base + (uint32_t)((hf * nkb + kb) * kSimABytes));
             const uint32_t d_addr = tmem + (uint32_t)((buf * 2 + hf) * kSimBN);
+            mma_bf16_ss(d_addr, da, db, idesc, kb != 0);
 #pragma unroll
-            for (int k = 0; k < kSimBK / 16; ++k) mma_bf16_ss(d_addr, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 1; k < kSimBK / 16; ++k) mma_bf16_ss_acc(d_addr, da + 2 * k, db + 2 * k, idesc);
           }
           if (cl > 1) mma_commit_mc(&tail->empty[st], cmask);
           else mma_commit(&tail->empty[st]);
         }
+        __syncwarp();
+        if (++st == nstages) { st = 0; ph ^= 1u; }
+      }
+      if (leader) {
         mma_commit(&tail->acc_full[buf]);
         SIM_TRACE(i, 1);
       }
+      __syncwarp();
     }
   } else {
     const int e = warp;

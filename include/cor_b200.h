@@ -260,6 +260,21 @@ int cor_val_post(const void* pred, int pred_dtype, int N, int H, int W, int Ho, 
 int cor_soft_metrics(const float* pred, const void* gt, int gt_dtype, float gt_scale, int N, long long total,
                      float smooth, float* metrics, void* work, cor_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Mask-logit producer: the hypernetwork product of the SAM decoder,
+ *   masks[b, t, p] = sum_c hyper_in[b, t0 + t, c] * upscaled[b, c, p]     lib/sam_model/mask_decoder.py:135-137
+ * for the T consumed tokens only (the reference computes all four and slices, :97-102), written in the dtype the
+ * segmentation-loss kernel reads.  hyper [B, T_all, C] f32, up [B, C, P] f32/bf16, out [B, T, P] f32/bf16;
+ * T <= 4, C <= 64, P % 4 == 0.  Backward in one pass over `up` and the logit gradient g [B, T, P]:
+ * d_up [B, C, P] (dtype of up; may be NULL) and d_hyper [B, T_all, C] f32 (zero rows for unused tokens);
+ * work: cor_hyper_logits_work_bytes() bytes of per-CTA partials, folded in fixed order.
+ * ---------------------------------------------------------------------------------------- */
+size_t cor_hyper_logits_work_bytes(int B, int T, int C, long long P);
+int cor_hyper_logits_fwd(const float* hyper, const void* up, int up_dtype, void* out, int out_dtype, int B, int T_all, int t0,
+                         int T, int C, long long P, cor_stream_t stream);
+int cor_hyper_logits_bwd(const float* hyper, const void* up, int up_dtype, const void* g, int g_dtype, void* d_up,
+                         float* d_hyper, int B, int T_all, int t0, int T, int C, long long P, void* work, cor_stream_t stream);
+
 /* ----------------------------------------------------------------------------------------------
  * (e) Multi-GPU exchange over NVLink peer memory (one process per GPU, one node) - the B200-native replacement of
  * the all-gather of the region rows and the reduce-scatter of their gradient around the similarity stage
