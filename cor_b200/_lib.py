@@ -16,6 +16,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "cor_b200.h")
 F32, BF16, U8 = 0, 1, 2
 ABI_VERSION = 2
 # terms of the segmentation loss (include/cor_b200.h COR_SEG_*)
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SIGMOID = range(4)
 SEG_WBCE, SEG_WIOU, SEG_DICE, SEG_BCE, SEG_IOU, SEG_WDICE, SEG_FOCAL, SEG_NTERMS = range(8)
 W_PLAIN, W_CLAMP, W_SIGMOID = 0, 1, 2
 
@@ -93,6 +94,10 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_infonce_bwd_umma", i, p, p, i, i, i, f, p, p, p, f, p, p, p, p)
         _sig(lib, "cor_topk", i, p, p, p, i, i, i, i, p, p, p)
         _sig(lib, "cor_l2_normalize", i, p, i, i, i, p, p, p, p)
+        _sig(lib, "cor_gemm_bf16_work_bytes", sz, i, i, i, i, i)
+        _sig(lib, "cor_gemm_bf16", i, p, i, ll, ll, p, i, ll, ll, i, i, i, i, f, p, i, p, p, p, i, ll, p, i, ll, p, i, p, p)
+        _sig(lib, "cor_cast_cat_bf16", i, p, i, p, i, ll, p, p)
+        _sig(lib, "cor_act_bwd", i, p, p, p, p, i, i, i, p, p, p)
         _sig(lib, "cor_hyper_logits_work_bytes", sz, i, i, i, ll)
         _sig(lib, "cor_hyper_logits_fwd", i, p, p, i, p, i, i, i, i, i, i, ll, p)
         _sig(lib, "cor_hyper_logits_bwd", i, p, p, i, p, i, p, p, i, i, i, i, i, ll, p, p)

@@ -1,0 +1,125 @@
+"""Linear layers on the tcgen05 GEMM of ``csrc/gemm_umma.cu`` (bf16 operands, fp32 accumulate), forward and backward.
+
+``linear(x, weight, bias, act, drop_mask)`` is ``drop_mask * act(x @ weight.T + bias)`` as ONE kernel (the bias,
+activation and dropout mask live in the GEMM epilogue); its backward is one element-wise kernel (``cor_act_bwd``: the
+epilogue's derivative, bf16 ``dZ`` and the bias gradient) and two more GEMMs that read the SAME buffers in the other
+orientation -- ``dX = dZ W`` takes ``W [out, in]`` as an MN-major operand, ``dW = dZ^T X`` takes both ``dZ`` and ``X``
+MN-major -- so nothing is ever transposed in memory.  Under bf16 autocast the reference's ``nn.Linear`` computes the
+same way (bf16 operands, fp32 accumulate, lib/support_branch.py:47-54 inside utils/trainer_v3_g.py:51).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CorError
+
+__all__ = ["gemm", "linear", "cast_bf16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_SIGMOID"]
+
+_ACTS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "sigmoid": ACT_SIGMOID}
+
+
+def cast_bf16(a: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 copy of ``a`` ([rows, c0] f32), or of ``cat(a, b, dim=-1)`` -- one kernel."""
+    dev = L.require_cuda(a, b)
+    a = a.float().contiguous()
+    rows, c0 = a.shape
+    c1 = 0
+    if b is not None:
+        b = b.float().contiguous()
+        if b.shape[0] != rows:
+            raise CorError(f"cast_bf16: row counts differ ({rows} vs {b.shape[0]})")
+        c1 = b.shape[1]
+    out = torch.empty((rows, c0 + c1), dtype=torch.bfloat16, device=dev)
+    ops._call("cor_cast_cat_bf16", dev, ops.ptr(a), c0, ops.ptr(b), c1, ops._ll(rows), ops.ptr(out))
+    return out
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False, b_mn: bool = False, batch: int = 1,
+         a_batch_rows: int = 0, b_batch_rows: int = 0, alpha: float = 1.0, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         emul: Optional[torch.Tensor] = None, colscale: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         out_dtype: torch.dtype = torch.float32, want_pre: bool = False, ksplit: int = 0):
+    """C[b][m][n] = epilogue(alpha * sum_k A[b](m,k) B[b](n,k)); see include/cor_b200.h (cor_gemm_bf16).  ``a`` / ``b`` are
+    2-D bf16 tensors; ``x_mn`` says the operand is stored [K, rows] instead of [rows, K].  Returns C [batch*M, N] (and the
+    bf16 pre-activation when ``want_pre``)."""
+    dev = L.require_cuda(a, b, bias, emul, colscale, residual)
+    if a.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or a.dim() != 2 or b.dim() != 2:
+        raise CorError("gemm: operands must be 2-D bf16 tensors")
+    a, b = a.contiguous(), b.contiguous()
+    lib = L.load()
+    C = torch.empty((batch * M, N), dtype=out_dtype, device=dev)
+    pre = torch.empty((batch * M, N), dtype=torch.bfloat16, device=dev) if want_pre else None
+    work = ops._work(lib.cor_gemm_bf16_work_bytes(M, N, K, batch, ksplit), dev)
+    res = residual.contiguous() if residual is not None else None
+    ops._call("cor_gemm_bf16", dev, ops.ptr(a), int(a_mn), ops._ll(a.shape[0]), ops._ll(a_batch_rows), ops.ptr(b), int(b_mn),
+              ops._ll(b.shape[0]), ops._ll(b_batch_rows), M, N, K, batch, ops._f(alpha), ops.ptr(bias), int(act), ops.ptr(emul),
+              ops.ptr(colscale), ops.ptr(res), (L.dtype_code(res) if res is not None else L.F32), ops._ll(N), ops.ptr(C), L.dtype_code(C),
+              ops._ll(N), ops.ptr(pre), int(ksplit), ops.ptr(work))
+    return (C, pre) if want_pre else C
+
+
+_w16_cache = {}
+
+
+def _weight_bf16(w: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a parameter, refreshed when the parameter is updated in place (optimizer step bumps ``_version``)."""
+    key = (w.data_ptr(), tuple(w.shape))
+    hit = _w16_cache.get(key)
+    if hit is not None and hit[0] == w._version:
+        return hit[1]
+    w16 = cast_bf16(w.detach().reshape(w.shape[0], -1))
+    _w16_cache[key] = (w._version, w16)
+    return w16
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, drop_mask, x2):
+        dev = L.require_cuda(x, weight, bias, drop_mask, x2)
+        rows = x.shape[0]
+        x16 = cast_bf16(x, x2)                       # [rows, K]; torch.cat((x, x2), -1) fused with the cast
+        w16 = _weight_bf16(weight)
+        N, K = w16.shape
+        if x16.shape[1] != K:
+            raise CorError(f"linear: input width {x16.shape[1]} != weight in_features {K}")
+        b32 = bias.float().contiguous() if bias is not None else None
+        m32 = drop_mask.float().contiguous() if drop_mask is not None else None
+        y, pre = gemm(x16, w16, rows, N, K, bias=b32, act=act, emul=m32, want_pre=True) if act == ACT_GELU else \
+            (gemm(x16, w16, rows, N, K, bias=b32, act=act, emul=m32), None)
+        ctx.save_for_backward(x16, w16, y, pre, m32)
+        ctx.cfg = (act, x.shape[1], x.requires_grad, x2 is not None and x2.requires_grad, weight.requires_grad,
+                   bias is not None and bias.requires_grad, x.dtype, weight.dtype, tuple(weight.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x16, w16, y, pre, m32 = ctx.saved_tensors
+        act, c0, need_x, need_x2, need_w, need_b, xdt, wdt, wshape = ctx.cfg
+        dev = y.device
+        rows, N = y.shape
+        K = x16.shape[1]
+        gy = gy.float().contiguous()
+        dz = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
+        db = torch.empty((N,), dtype=torch.float32, device=dev) if need_b else None
+        # relu / sigmoid differentiate through the stored OUTPUT: with a dropout mask folded in, y = mask * act(z), and
+        # y > 0 <=> act(z) > 0 on kept elements (dropped ones get zero gradient from the mask factor anyway); sigmoid is
+        # never combined with a mask in the reference
+        ops._call("cor_act_bwd", dev, ops.ptr(gy), ops.ptr(y), ops.ptr(pre), ops.ptr(m32), int(act), rows, N, ops.ptr(dz), ops.ptr(db))
+        gx = gx2 = gw = None
+        if need_x or need_x2:
+            g_in = gemm(dz, w16, rows, K, N, b_mn=True)                   # dX = dZ W : W [N, K] read as the MN-major B (k = out features)
+            gx = g_in[:, :c0].to(xdt) if need_x else None
+            gx2 = g_in[:, c0:].to(xdt) if need_x2 else None
+        if need_w:
+            gw = gemm(dz, x16, N, K, rows, a_mn=True, b_mn=True).view(wshape).to(wdt)   # dW = dZ^T X : both operands MN-major (k = rows)
+        return gx, gw, db, None, None, gx2
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+           drop_mask: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``drop_mask * act(cat(x, x2) @ weight.T + bias)`` -> f32 [rows, out_features]; x [rows, in] (any leading shape is
+    flattened by the caller).  ``drop_mask`` holds 0 or 1/(1-p) per element (what ``F.dropout`` multiplies by)."""
+    return _LinearFn.apply(x, weight, bias, _ACTS[act], drop_mask, x2)

@@ -261,6 +261,35 @@ int cor_soft_metrics(const float* pred, const void* gt, int gt_dtype, float gt_s
                      float smooth, float* metrics, void* work, cor_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * General bf16 GEMM on tcgen05 tensor cores with a fused epilogue (csrc/gemm_umma.cu): the building block of the
+ * learned modules either side of the region path -- the 1x1 convolutions / point-wise MLPs of GenerateMaskAdapterMap
+ * (lib/support_model/mask_adapter.py:97-223) and the linear layers of the composed-query head
+ * (lib/support_model/cir_feature_fuse.py:20-43, lib/support_branch.py:47-54), forward and backward.
+ *   C[b][m][n] = epi( alpha * sum_k A[b](m,k) B[b](n,k) ),  epi: + bias[n]; (pre = v, bf16, optional); act; * emul[b][m][n]
+ *   (dropout mask, optional); * colscale[n]; + residual[b][m][n]; store f32 / bf16 with row pitch ldc.
+ *   Operand orientation (x_mn): 0 = K-major, stored [rows][K]; 1 = MN-major, stored [K][rows].  Both are 2-D bf16 tensors of
+ *   x_rows_total rows (K-major: x_rows_total x K; MN-major: x_rows_total x rows, x_rows_total = batch * K); batch entry b
+ *   starts at row b * x_batch_rows (0 = the operand is shared by every batch entry).  Row pitches must be multiples of 16 B.
+ *   ksplit: 0 = automatic split-K when there are few output tiles (weight-gradient GEMMs), >0 forces it; split partials are
+ *   folded in fixed order.  work: cor_gemm_bf16_work_bytes() bytes.
+ * ---------------------------------------------------------------------------------------- */
+enum { COR_ACT_NONE = 0, COR_ACT_RELU = 1, COR_ACT_GELU = 2, COR_ACT_SIGMOID = 3 };
+size_t cor_gemm_bf16_work_bytes(int M, int N, int K, int batch, int ksplit);
+int cor_gemm_bf16(const void* A, int a_mn, long long a_rows_total, long long a_batch_rows, const void* B, int b_mn,
+                  long long b_rows_total, long long b_batch_rows, int M, int N, int K, int batch, float alpha, const float* bias,
+                  int act, const float* emul, const float* colscale, const void* residual, int res_dtype, long long ldr, void* C,
+                  int c_dtype, long long ldc, void* pre_bf16, int ksplit, void* work, cor_stream_t stream);
+
+/* Operand prep and epilogue backward for cor_gemm_bf16 (csrc/ew.cu).
+ *   cor_cast_cat_bf16: out[r] = bf16(concat(a[r][0:c0], b[r][0:c1])) (b NULL, c1 = 0: a plain cast) -- torch.cat at
+ *                      cir_feature_fuse.py:49,54 fused with the operand cast.
+ *   cor_act_bwd: dz = dy * emul * act'(.) as bf16 [M,N] and db[n] = sum_m dz (rows in order).  y_f32 = activation output
+ *                before the dropout mask (relu, sigmoid), pre_bf16 = pre-activation saved by the GEMM (gelu). */
+int cor_cast_cat_bf16(const float* a, int c0, const float* b, int c1, long long rows, void* out_bf16, cor_stream_t stream);
+int cor_act_bwd(const float* dy, const float* y_f32, const void* pre_bf16, const float* emul, int act, int M, int N,
+                void* dz_bf16, float* db, cor_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Mask-logit producer: the hypernetwork product of the SAM decoder,
  *   masks[b, t, p] = sum_c hyper_in[b, t0 + t, c] * upscaled[b, c, p]     lib/sam_model/mask_decoder.py:135-137
  * for the T consumed tokens only (the reference computes all four and slices, :97-102), written in the dtype the

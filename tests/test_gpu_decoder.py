@@ -34,7 +34,7 @@ def test_logits_and_seg_loss_matches_two_step_path():
     from cor_b200.mask_decoder import logits_and_seg_loss
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(9)
-    h = 0.3 * torch.randn(2, 4, 32, device=dev, generator=g, requires_grad=True)
+    h = (0.3 * torch.randn(2, 4, 32, device=dev, generator=g)).requires_grad_(True)
     up = torch.randn(2, 32, 256, 256, device=dev, generator=g, requires_grad=True)
     mask = (torch.rand(2, 1, 1024, 1024, device=dev, generator=g) > 0.6).float()
     loss, logits = logits_and_seg_loss(h, up, mask)
