@@ -6,15 +6,18 @@
 // Neither S nor P ever exists in global memory.  ONE kernel serves both products, with the roles of the operands
 // swapped (mode 0: X = queries, Y = regions, G = dQ;  mode 1: X = regions, Y = queries, G = dR):
 //
-//   a CTA keeps 128 X rows resident in shared memory and walks Y tiles of 128 rows:
-//     GEMM 1   S^(X)[128 x 128] = X Y^T            A = X (K-major, TMA, SW128)      B = Y tile (K-major)
+//   a CTA keeps 128 X rows resident in shared memory and walks Y tiles of 64 rows:
+//     GEMM 1   S^(X)[128 x 64] = X Y^T             A = X (K-major, TMA, SW128)      B = Y tile (K-major)
 //     epilogue the thread that owns TMEM lane x turns its S row into bf16 coefficients and stores them into
 //              shared memory in the canonical K-major SW128 layout (manual swizzle) -> A operand of GEMM 2
-//     GEMM 2   G[128 x D] += P[128 x 128] Y         A = P (K-major, K = Y rows)      B = THE SAME Y TILE, read
+//     GEMM 2   G[128 x D] += P[128 x 64] Y          A = P (K-major, K = Y rows)      B = THE SAME Y TILE, read
 //              as an MN-major operand (its [y][d] rows are K = y, N = d with d contiguous; SW128 atoms are the
 //              8-row x 128-byte groups TMA wrote; LBO = distance between 64-wide d blocks, SBO = 1024 B)
-//   so every Y byte fetched from L2 feeds both GEMMs: 64 KB per 2 x 4.2 MFLOP tile.
-//   TMEM: S double-buffered (2 x 128 columns) so GEMM 1 of tile i+1 overlaps the epilogue of tile i; G in 256 columns.
+//   so every Y byte fetched from L2 feeds both GEMMs.  A Y tile stays in shared memory from its load to the end of its
+//   GEMM 2, i.e. through a whole TMA -> GEMM 1 -> epilogue -> GEMM 2 round trip: the tiles are kept SMALL (64 rows, 32 KB
+//   at D = 256) so that FOUR of them fit beside X -- with two 128-row slots the next load could only start when a GEMM 2
+//   finished and the tensor pipe idled through every load latency (measured 5 700 cycles per 128 rows against 2 048 of
+//   tensor work).  TMEM: S double-buffered (2 x 64 columns), P double-buffered in shared memory, G in 256 columns.
 //
 // Warp roles (320 threads): 0..7 = epilogue (warp w owns TMEM lane quarter w % 4 and column half w / 4, i.e. exactly one
 // 128-byte row of one P k-block per thread), 8 = TMA producer, 9 = TMEM owner + MMA issuer (highest warp ids: the
@@ -29,15 +32,16 @@ namespace cor {
 using namespace umma;
 
 constexpr int kNbM = 128;                  // X rows per CTA (UMMA M)
-constexpr int kNbN = 128;                  // Y rows per tile (GEMM 1 N, GEMM 2 K)
+constexpr int kNbN = 64;                   // Y rows per tile (GEMM 1 N, GEMM 2 K)
 constexpr int kNbBK = 64;
-constexpr int kNbBlk = kNbM * kNbBK * 2;   // 16 KB: one 64-wide k-block of 128 rows
-constexpr int kNbMaxSlots = 3;
+constexpr int kNbBlk = kNbM * kNbBK * 2;   // 16 KB: one 64-wide k-block of the 128 X rows; also one P buffer [128 x 64]
+constexpr int kNbYBlk = kNbN * kNbBK * 2;  // 8 KB: one 64-wide k-block of a Y tile
+constexpr int kNbMaxSlots = 4;
 constexpr int kNbTmaWarp = 8, kNbMmaWarp = 9;
 constexpr int kNbPrefetch = 3;
 
 struct NceSmemTail {
-  uint64_t xfull, yfull[kNbMaxSlots], yempty[kNbMaxSlots], s_full[2], s_empty[2], p_full, p_empty, g_full;
+  uint64_t xfull, yfull[kNbMaxSlots], yempty[kNbMaxSlots], s_full[2], s_empty[2], p_full[2], p_empty[2], g_full;
   uint32_t tmem_base;
 };
 
@@ -78,8 +82,8 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   uint8_t* x_smem = base;                                                    // nkb x 16 KB
-  uint8_t* y_smem = x_smem + (size_t)a.nkb * kNbBlk;                         // nslots x nkb x 16 KB
-  uint8_t* p_smem = y_smem + (size_t)a.nslots * a.nkb * kNbBlk;              // 2 x 16 KB (k-blocks y 0..63, 64..127)
+  uint8_t* y_smem = x_smem + (size_t)a.nkb * kNbBlk;                         // nslots x nkb x 8 KB
+  uint8_t* p_smem = y_smem + (size_t)a.nslots * a.nkb * kNbYBlk;             // 2 buffers x 16 KB
   NceSmemTail* tail = reinterpret_cast<NceSmemTail*>(p_smem + 2 * kNbBlk);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,8 +98,7 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
     mbar_init(&tail->xfull, 1);
     for (int i = 0; i < a.nslots; ++i) { mbar_init(&tail->yfull[i], 1); mbar_init(&tail->yempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tail->s_full[i], 1); mbar_init(&tail->s_empty[i], 8); }
-    mbar_init(&tail->p_full, 8);
-    mbar_init(&tail->p_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tail->p_full[i], 8); mbar_init(&tail->p_empty[i], 1); }
     mbar_init(&tail->g_full, 1);
     fence_barrier_init();
   }
@@ -118,9 +121,9 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
           for (int kb = 0; kb < a.nkb; ++kb) tma_prefetch_2d(&tmY, kb * kNbBK, (t + kNbPrefetch * (int)gridDim.x) * kNbN);
         const int slot = i % a.nslots;
         mbar_wait(&tail->yempty[slot], ((i / a.nslots) & 1) ^ 1);
-        mbar_expect_tx(&tail->yfull[slot], (uint32_t)(a.nkb * kNbBlk));
+        mbar_expect_tx(&tail->yfull[slot], (uint32_t)(a.nkb * kNbYBlk));
         for (int kb = 0; kb < a.nkb; ++kb)
-          tma_load_2d(y_smem + (size_t)(slot * a.nkb + kb) * kNbBlk, &tmY, &tail->yfull[slot], kb * kNbBK, t * kNbN, kEvictLast);
+          tma_load_2d(y_smem + (size_t)(slot * a.nkb + kb) * kNbYBlk, &tmY, &tail->yfull[slot], kb * kNbBK, t * kNbN, kEvictLast);
       }
     }
   } else if (warp == kNbMmaWarp) {
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
         if (leader) {
           for (int kb = 0; kb < a.nkb; ++kb) {
             const uint64_t da = make_desc_sw128(x_base + (uint32_t)(kb * kNbBlk));
-            const uint64_t db = make_desc_sw128(y_base + (uint32_t)((slot * a.nkb + kb) * kNbBlk));
+            const uint64_t db = make_desc_sw128(y_base + (uint32_t)((slot * a.nkb + kb) * kNbYBlk));
             mma_bf16_ss(tmem + (uint32_t)(buf * kNbN), da, db, idesc1, kb != 0);
 #pragma unroll
             for (int k = 1; k < kNbBK / 16; ++k) mma_bf16_ss_acc(tmem + (uint32_t)(buf * kNbN), da + 2 * k, db + 2 * k, idesc1);
@@ -149,20 +152,21 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
         __syncwarp();
       };
       gemm1(0);
+      if (n_my > 1) gemm1(1);
       for (int i = 0; i < n_my; ++i) {
-        if (i + 1 < n_my) gemm1(i + 1);            // overlaps the epilogue of tile i
-        const int slot = i % a.nslots;
-        mbar_wait(&tail->p_full, i & 1);
+        if (i + 2 < n_my) gemm1(i + 2);            // needs only the S buffer of tile i, which the epilogue frees early
+        const int slot = i % a.nslots, pb = i & 1;
+        mbar_wait(&tail->p_full[pb], (i >> 1) & 1);
         tc_fence_after();
         if (leader) {
-          // B = the Y tile as an MN-major operand: N = d (nkb blocks of 64, kNbBlk apart), K = y rows (8-row groups 1024 B apart)
-          const uint64_t db0 = make_desc_sw128_mn(y_base + (uint32_t)(slot * a.nkb * kNbBlk), kNbBlk, 1024);
-          const uint64_t dp0 = make_desc_sw128(p_base), dp1 = make_desc_sw128(p_base + kNbBlk);
+          // B = the Y tile as an MN-major operand: N = d (nkb blocks of 64, kNbYBlk apart), K = y rows (8-row groups 1024 B apart)
+          const uint64_t db0 = make_desc_sw128_mn(y_base + (uint32_t)(slot * a.nkb * kNbYBlk), kNbYBlk, 1024);
+          const uint64_t dp0 = make_desc_sw128(p_base + (uint32_t)(pb * kNbBlk));
           mma_bf16_ss(tmem_g, dp0, db0, idesc2, i != 0);
 #pragma unroll
           for (int j = 1; j < kNbN / 16; ++j)       // 16 y rows = 2048 B = 128 x 16 B
-            mma_bf16_ss_acc(tmem_g, (j < 4 ? dp0 : dp1) + 2 * (j & 3), db0 + (uint64_t)(j * 128), idesc2);
-          mma_commit(&tail->p_empty);
+            mma_bf16_ss_acc(tmem_g, dp0 + 2 * j, db0 + (uint64_t)(j * 128), idesc2);
+          mma_commit(&tail->p_empty[pb]);
           mma_commit(&tail->yempty[slot]);
         }
         __syncwarp();
@@ -188,61 +192,55 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
     for (int i = 0; i < n_my; ++i) {
       const int t = blockIdx.x + i * gridDim.x;
       const int buf = i & 1;
-      const int y0 = t * kNbN + half * 64;          // first Y row (S column) this thread handles
-      // mode 1: the columns are queries -- lane l fetches the constants of column y0 + l (+32), shuffled out below
-      float nl_a = 0.f, nl_b = 0.f;
-      int tg_a = -1, tg_b = -1;
+      const int y0 = t * kNbN + half * 32;          // first Y row (S column) this thread handles
+      // mode 1: the columns are queries -- lane l fetches the constants of column y0 + l, shuffled out below
+      float nl_a = 0.f;
+      int tg_a = -1;
       if (a.mode == 1) {
-        const int qa = y0 + lane, qb = y0 + 32 + lane;
+        const int qa = y0 + lane;
         nl_a = qa < a.Nq ? -__ldg(a.lse + qa) * log2e : -INFINITY;      // exp2(-inf) = 0: columns past Nq contribute nothing
-        nl_b = qb < a.Nq ? -__ldg(a.lse + qb) * log2e : -INFINITY;
         tg_a = qa < a.Nq ? (int)__ldg(a.targets + qa) : -1;
-        tg_b = qb < a.Nq ? (int)__ldg(a.targets + qb) : -1;
       }
       mbar_wait(&tail->s_full[buf], (i >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * kNbN + half * 64);
-      uint32_t va[32], vb[32];
+      const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * kNbN + half * 32);
+      uint32_t va[32];
       tmem_ld_32(taddr, va);
-      tmem_ld_32(taddr + 32u, vb);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->s_empty[buf]);          // S is in registers: GEMM 1 of tile i+2 may overwrite the buffer
-      uint32_t w[32];                                            // 64 bf16 coefficients = this thread's 128-byte P row
-      auto coefs = [&](uint32_t (&v)[32], int cbase, float nl_l, int tg_l, int wofs) {
+      uint32_t w[16];                                            // 32 bf16 coefficients = this thread's half of a 128-byte P row
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float n0, n1;
-          int hit0, hit1;
-          if (a.mode == 0) {
-            n0 = n1 = my_nl;
-            hit0 = (cbase + 2 * j == my_tg);
-            hit1 = (cbase + 2 * j + 1 == my_tg);
-          } else {
-            n0 = __shfl_sync(0xffffffffu, nl_l, 2 * j);
-            n1 = __shfl_sync(0xffffffffu, nl_l, 2 * j + 1);
-            hit0 = (__shfl_sync(0xffffffffu, tg_l, 2 * j) == xg);
-            hit1 = (__shfl_sync(0xffffffffu, tg_l, 2 * j + 1) == xg);
-          }
-          float c0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), a.c2, n0));
-          float c1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), a.c2, n1));
-          if (hit0) c0 -= 1.f;
-          if (hit1) c1 -= 1.f;
-          w[wofs + j] = pack_bf16x2_rn(c0 * gscale, c1 * gscale);
+      for (int j = 0; j < 16; ++j) {
+        float n0, n1;
+        int hit0, hit1;
+        if (a.mode == 0) {
+          n0 = n1 = my_nl;
+          hit0 = (y0 + 2 * j == my_tg);
+          hit1 = (y0 + 2 * j + 1 == my_tg);
+        } else {
+          n0 = __shfl_sync(0xffffffffu, nl_a, 2 * j);
+          n1 = __shfl_sync(0xffffffffu, nl_a, 2 * j + 1);
+          hit0 = (__shfl_sync(0xffffffffu, tg_a, 2 * j) == xg);
+          hit1 = (__shfl_sync(0xffffffffu, tg_a, 2 * j + 1) == xg);
         }
-      };
-      coefs(va, y0, nl_a, tg_a, 0);
-      coefs(vb, y0 + 32, nl_b, tg_b, 16);
-      // P row -> shared memory, K-major SW128: k-block `half`, 16-byte chunk c of row r at c ^ (r & 7)
-      mbar_wait(&tail->p_empty, (i & 1) ^ 1);                     // GEMM 2 of tile i-1 has consumed the previous P
-      uint8_t* prow = p_smem + half * kNbBlk + row * 128;
+        float c0 = ex2_approx(fmaf(__uint_as_float(va[2 * j]), a.c2, n0));
+        float c1 = ex2_approx(fmaf(__uint_as_float(va[2 * j + 1]), a.c2, n1));
+        if (hit0) c0 -= 1.f;
+        if (hit1) c1 -= 1.f;
+        w[j] = pack_bf16x2_rn(c0 * gscale, c1 * gscale);
+      }
+      // P row -> shared memory, K-major SW128: 16-byte chunk c of row r at c ^ (r & 7); this thread owns chunks half*4 .. +3
+      const int pb = i & 1;
+      mbar_wait(&tail->p_empty[pb], ((i >> 1) & 1) ^ 1);        // GEMM 2 of tile i-2 has consumed this buffer
+      uint8_t* prow = p_smem + pb * kNbBlk + row * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (row & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
       fence_proxy_async();                                        // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->p_full);
+      if (lane == 0) mbar_arrive(&tail->p_full[pb]);
     }
     // ---- drain G: this thread's X row, columns [half * D/2, +D/2) ----
     if (n_my > 0) {
@@ -297,12 +295,12 @@ static int nce_launch(const void* X, const void* Y, int Nx, int Ny, int Nq, int 
   if (rc) return rc;
   rc = encode_tmap_bf16_2d(&tmY, Y, (uint64_t)Ny, (uint64_t)D, kNbN, kNbBK);
   if (rc) return rc;
-  // shared memory: X (nkb blocks) + P (2 blocks) + as many whole-Y-tile slots as fit (2 or 3)
+  // shared memory: X (nkb blocks) + 2 P buffers + as many whole-Y-tile slots as fit (4 at D = 256)
   const size_t fixed = (size_t)(nkb + 2) * kNbBlk + sizeof(NceSmemTail) + 1024;
-  int nslots = (int)((227 * 1024 - fixed) / ((size_t)nkb * kNbBlk));
+  int nslots = (int)((227 * 1024 - fixed) / ((size_t)nkb * kNbYBlk));
   if (nslots > kNbMaxSlots) nslots = kNbMaxSlots;
   COR_REQUIRE(nslots >= 2, "cor_infonce_bwd_umma: shared memory budget (D=%d)", D);
-  const size_t smem = fixed + (size_t)nslots * nkb * kNbBlk;
+  const size_t smem = fixed + (size_t)nslots * nkb * kNbYBlk;
   COR_CUDA(cudaFuncSetAttribute(nce_bwd_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NceArgs a;
   a.Nx = Nx; a.Ny = Ny; a.Nq = Nq; a.nkb = nkb; a.nslots = nslots; a.mode = mode;
