@@ -140,6 +140,19 @@ class _FusedStepFn(torch.autograd.Function):
         side = _side_stream(dev) if _overlap_enabled() else None
         if side is not None:
             side.wait_stream(cur)
+        # multi-GPU: the bf16 rows land directly in this rank's peer-mapped buffer (cor_b200/peer.py), else in a local one.
+        # "Have my peers finished reading what I published last step?" is asked HERE, on the side stream at the very
+        # start of the step (one 32-thread CTA polling local flags): by the time the row epilogue needs the answer the
+        # 0.7 ms mask resample has gone by, so the wait never sits on the critical path.
+        rank, ws = cdist.world()
+        px = peer.get_exchange(B * M, Cc, dev) if (gather and ws > 1 and os.environ.get("COR_STEP_BWD", "reduce_scatter") != "local") else None
+        ev_px = None
+        if px is not None:
+            with torch.cuda.stream(side if side is not None else cur):
+                px.before_produce(0)
+                if side is not None:
+                    ev_px = torch.cuda.Event()
+                    ev_px.record(side)
         q16 = torch.empty((B, comb_c.shape[1]), dtype=torch.bfloat16, device=dev)
         ev_q = None
         with torch.cuda.stream(side if side is not None else cur):
@@ -160,12 +173,9 @@ class _FusedStepFn(torch.autograd.Function):
         part = torch.empty((ks, B, Rp, Cc), **f32)
         call("cor_pool_umma_fwd", dev, ptr(emb_c), ptr(w16), B, Cc, P, Rp, ptr(part))
         fg = torch.empty((B * M, Cc), **f32)
-        # multi-GPU: the bf16 rows land directly in this rank's peer-mapped buffer (cor_b200/peer.py), else in a local one
-        rank, ws = cdist.world()
-        px = peer.get_exchange(B * M, Cc, dev) if (gather and ws > 1 and os.environ.get("COR_STEP_BWD", "reduce_scatter") != "local") else None
         fg16 = px.pub if px is not None else torch.empty((B * M, Cc), dtype=torch.bfloat16, device=dev)
-        if px is not None:
-            px.before_produce(0)
+        if ev_px is not None:
+            cur.wait_event(ev_px)
         inv_fg = torch.empty((B * M,), **f32)
         split = B * Rp * Cc
         call("cor_rows_finalize", dev, ptr(part), M, _ll(Rp * Cc), ks, _ll(split), ptr(stats[:, 3:]), 4, _f(1e-8), B * M, Cc, 1, 1,
@@ -276,6 +286,17 @@ class _FusedStepFn(torch.autograd.Function):
             return gp
 
         px = ctx.px
+        ev_px = None
+        if px is not None and ws > 1 and q_all is None:
+            # same idea as in the forward: ask early, on the side stream, whether the peers are done with last step's `gall`
+            if side is not None:
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    px.before_produce(1)
+                    ev_px = torch.cuda.Event()
+                    ev_px.record(side)
+            else:
+                px.before_produce(1)
         if px is None or side is not None:
             g_pred = seg_bwd()               # side stream: runs underneath the InfoNCE / pooling backward
         # InfoNCE backward first: it WRITES g_regions (this rank's rows) and g_queries ...
@@ -291,8 +312,8 @@ class _FusedStepFn(torch.autograd.Function):
             call("cor_infonce_bwd", dev, ptr(fg16), ptr(q_all), ptr(tgt_all), ptr(lse_all), n_local, ws * B, Cc, _f(inv_tau), ptr(g),
                  _f(float(ws) * nce_weight), ptr(g_regions), None, None)
         elif ws > 1:
-            if px is not None:
-                px.before_produce(1)
+            if ev_px is not None:
+                cur.wait_event(ev_px)
             g_all = px.gall if px is not None else torch.empty((Nr, Cc), **f32)
             call("cor_infonce_bwd", dev, ptr(r16), ptr(q16), ptr(targets), ptr(lse), Nr, B, Cc, _f(inv_tau), ptr(g), _f(nce_weight),
                  ptr(g_all), ptr(g_q), ptr(work))
