@@ -349,23 +349,25 @@ def bind_to_gpu_numa(local):
     return info
 
 
-def pcie_h2d_gbs(dev, nbytes=1 << 30, iters=3):
-    """A bare pinned-host -> device cudaMemcpyAsync of `nbytes`, timed with CUDA events (best of `iters`): the platform
-    ceiling of the e2e leg on this GPU's PCIe link.  Every rank runs it at the same time (the caller barriers first), so
-    at N > 1 the figure includes whatever the host side loses to sharing."""
+def pcie_h2d_gbs(dev, nbytes=1 << 30, copies=8):
+    """Bare pinned-host -> device cudaMemcpyAsync: `copies` back-to-back copies of `nbytes` timed as ONE interval with
+    CUDA events (after one warm-up copy), i.e. the SUSTAINED rate while every other rank does the same (the caller
+    barriers first) -- the platform ceiling of the e2e leg.  (A best-of-N of single copies, as in round 1's first
+    version of this probe, lets each rank catch a moment when the GPU sharing its PCIe uplink is idle and reads high.)"""
     src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
     src.fill_(1)                       # first touch on this rank's (NUMA-bound) CPUs
     dst = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    best = 0.0
-    for _ in range(iters + 1):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+    dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(copies):
         dst.copy_(src, non_blocking=True)
-        b.record()
-        torch.cuda.synchronize()
-        best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+    b.record()
+    torch.cuda.synchronize()
+    gbs = copies * nbytes / (a.elapsed_time(b) * 1e-3) / 1e9
     del src, dst
-    return best
+    return gbs
 
 
 def l2_flush(buf):
@@ -432,6 +434,45 @@ def secondary_tensor_lines(dev, tc_burst, hbm_peak, iters=10):
                                               "achieved_tflops": 8.0 * Nq * Nr * D / (med * 1e-3) / 1e12}
     except Exception as e:  # noqa: BLE001
         out["infonce_fwd_bwd_1024x102400"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:   # the tensor-core backward alone (dQ and dR launches of csrc/nce_bwd_umma.cu), bare C-ABI call
+        from cor_b200 import _lib as L
+        lib = L.load()
+        Nq = 1024
+        q16 = torch.nn.functional.normalize(torch.randn(Nq, D, device=dev, generator=g), dim=-1).bfloat16()
+        tg = (torch.arange(Nq, device=dev) * 97) % Nr
+        _, lse = ops._sim_forward(r16, q16, 1.0 / 0.07, False, True, "umma")
+        gl = torch.ones(1, device=dev)
+        gq, gr = torch.empty(Nq, D, device=dev), torch.empty(Nr, D, device=dev)
+        work = ops._work(lib.cor_infonce_bwd_umma_work_bytes(Nq, Nr, D), dev)
+        med, best = timed(lambda: ops._call("cor_infonce_bwd_umma", dev, ops.ptr(r16), ops.ptr(q16), Nr, Nq, D, ops._f(1.0 / 0.07), ops.ptr(lse),
+                                            ops.ptr(tg), ops.ptr(gl), ops._f(1.0), ops.ptr(gr), ops.ptr(gq), ops.ptr(work)), n=5)
+        fl = 8.0 * Nq * Nr * D           # S recomputed for each product + the two products
+        out["nce_bwd_umma_kernel_1024x102400"] = {"what": "InfoNCE backward dQ + dR on tcgen05: S tile recomputed, P formed in registers and fed back through "
+                                                          "shared memory; no S, no P in HBM, no library GEMM", "bound": "tensor", "ms": med, "ms_best": best,
+                                                  "flops": fl, "achieved_tflops": fl / (med * 1e-3) / 1e12, "peak": tc_burst, "unit": "TFLOP/s",
+                                                  "frac": fl / (med * 1e-3) / 1e12 / tc_burst}
+        del gq, gr, work
+    except Exception as e:  # noqa: BLE001
+        out["nce_bwd_umma_kernel_1024x102400"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    try:   # the segmentation loss alone (what train_stage calls every step, utils/loss_func.py:5-32), CUDA-graph replay
+        for Bs in (16, 128):
+            pred = torch.randn(Bs, 1, 256, 256, device=dev, generator=g).bfloat16()
+            mask = (torch.rand(Bs, 1, 1024, 1024, device=dev, generator=g) > 0.5).float()
+            for _ in range(3):
+                ops.seg_loss(pred, mask)
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                ops.seg_loss(pred, mask)
+            med, best = timed(gph.replay)
+            alg, sect = Bs * 65536 * 18, Bs * 65536 * 34
+            out[f"seg_loss_fwd_B{Bs}"] = {"what": "wbce_with_wiou_loss forward incl. the 1024->256 target resample: strip kernel + finalize (+ the wrapper's two "
+                                                  "8-float copies), one graph replay", "bound": "hbm", "ms": med, "ms_best": best, "algorithmic_bytes": alg,
+                                          "sector_floor_bytes": sect, "achieved_gbs": alg / (med * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                          "frac": alg / (med * 1e-3) / 1e9 / hbm_peak, "frac_of_sector_floor": sect / (med * 1e-3) / 1e9 / hbm_peak}
+            del gph, pred, mask
+    except Exception as e:  # noqa: BLE001
+        out["seg_loss_fwd"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     try:
         gal = r32[:4096].contiguous()
         qs = torch.nn.functional.normalize(torch.randn(256, D, device=dev, generator=g), dim=-1)
@@ -641,6 +682,17 @@ def main():
         bufs.run(host, **kw)
     s1.record()
     barrier()
+    # how much of a step is the copy: the same loads alone, events around them (max over ranks)
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        bufs.load(host)
+    c1.record()
+    barrier()
+    h2d_t = torch.tensor([c0.elapsed_time(c1) / 3], device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_t, op=dist.ReduceOp.MAX)
+    h2d_ms = float(h2d_t)
     wall = (time.perf_counter() - t0) / e2e_steps
     e2e_ms = torch.tensor([max(s0.elapsed_time(s1) / e2e_steps, wall * 1e3)], device=dev)
     if world > 1:
@@ -708,7 +760,9 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": bufs.h2d_bytes, "d2h_bytes_per_step": 4,
                         "ms_per_step": float(e2e_ms), "steps": e2e_steps, "numa_local_cpus": numa["cpus"], "numa_node": numa["numa_node"],
                         "numa_how": numa["how"], "pcie_gbs_per_gpu": pcie_all,
-                        "pcie_note": "bare pinned cudaMemcpyAsync H2D of 1 GiB on every GPU at once (best of 3): the platform ceiling of this leg",
+                        "pcie_note": "8 back-to-back pinned cudaMemcpyAsync H2D copies of 1 GiB on every GPU at once, timed as one interval: the "
+                                     "sustained platform ceiling of this leg (GPUs that share a PCIe uplink halve each other)",
+                        "h2d_ms_per_step": h2d_ms, "frac_of_pcie_bound": (bufs.h2d_bytes / (min(pcie_all) * 1e9) * 1e3) / float(e2e_ms),
                         "pcie_bound_ms_per_step": bufs.h2d_bytes / (min(pcie_all) * 1e9) * 1e3},
                 "gpu_launches": launches, "graphed": graphed, "roofline": roofline, "secondary_kernels": secondary, "variants": variants,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},

@@ -19,6 +19,10 @@ int launch_lse_combine(const float* part, int Nq, int nparts, int qt, float* lse
 int sim_umma_launch(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, float* S, float* lse, void* work,
                     int* nparts, int* qt, cudaStream_t st);
 
+// same, queries held in tensor memory (sim_umma_ts.cu); log-sum-exp partials only: [qtile][*nparts][256][2] in `work`
+int sim_umma_ts_launch(const void* regions, const void* queries, int Nr, int Nq, int D, float inv_tau, void* work, int* nparts,
+                       cudaStream_t st);
+
 #define COR_REQUIRE(cond, ...)          \
   do {                                  \
     if (!(cond)) {                      \

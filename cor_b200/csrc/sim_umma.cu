@@ -354,6 +354,22 @@ static int sim_umma_launch_impl(const void* regions, const void* queries, int Nr
   // kernel is paced by the TMEM read-out of the S tile, not by L2 -- so the default stays 1; COR_SIM_CLUSTER=2|4 enables it.
   int cl = 1;
   if (const char* e = getenv("COR_SIM_CLUSTER")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && qtiles % v == 0) cl = v; }
+  // log-sum-exp only (the InfoNCE forward): the kernel that keeps the queries in tensor memory (sim_umma_ts.cu) -- the
+  // tensor pipe is no longer throttled by shared-memory bandwidth.  COR_SIM_TS=0 keeps this file's kernel (A/B).
+  {
+    const char* e = getenv("COR_SIM_TS");
+    if (want_lse && !S && !coef.P && cl == 1 && !(e && atoi(e) == 0)) {
+      int gx_ts = 0;
+      int rc_ts = sim_umma_ts_launch(regions, queries, Nr, Nq, D, inv_tau, work, &gx_ts, st);
+      if (rc_ts) return rc_ts;
+      if (nparts) {
+        *nparts = gx_ts;
+        *qt = kSimBM;
+        return COR_OK;
+      }
+      return launch_lse_combine((const float*)work, Nq, gx_ts, kSimBM, lse, st);
+    }
+  }
   CUtensorMap tmQ, tmR;
   int rc = umma::encode_tmap_bf16_2d(&tmQ, queries, (uint64_t)Nq, (uint64_t)D, kSimHalf, kSimBK);
   if (rc) return rc;

@@ -10,6 +10,9 @@ The reference has no plugin registry; its hot path is reached through Python nam
       -> so SupportBranch(mask_pooling="MaskedPooling"|"MaskAdapterPooling") (lib/support_branch.py:29-40)
          built through build_model_with_query_support_feat(..., mask_pooling=) (lib/build_model.py:14-20,72)
          runs the CUDA tails with its own parameters and state_dict untouched.
+  lib.support_branch.SupportBranch.forward                  (composed-query head on the tcgen05 GEMM, support_head.py)
+  lib.sam_model.mask_decoder.MaskDecoder.predict_masks      (hypernetwork product on csrc/hyper_logits.cu)
+      -> both use the module's own parameters in place; opt out with install(head=False, decoder=False).
 
 Nothing else in the reference changes: my_train_a.py / trainer loops / checkpoints keep working.
 """
@@ -22,7 +25,9 @@ import torch.nn.functional as F
 
 from . import loss_func as _lf
 from . import mask_adapter as _ma
+from . import mask_decoder as _md
 from . import metrics as _mt
+from . import support_head as _sh
 
 _LOSS_NAMES = ("wbce_with_wiou_loss", "mask_pooling", "fg_feat_similarity_loss", "bg_feat_similarity_loss")
 _METRIC_NAMES = ("compute_dice", "compute_mae", "compute_iou", "compute_mdice", "compute_miou")
@@ -50,7 +55,8 @@ def _maybe(name):
 
 
 def install(loss_module="utils.loss_func", trainer_module="utils.trainer_v3_g",
-            adapter_module="lib.support_model.mask_adapter"):
+            adapter_module="lib.support_model.mask_adapter", branch_module="lib.support_branch",
+            decoder_module="lib.sam_model.mask_decoder", head=True, decoder=True):
     """Rebind the reference's hot-path names to the CUDA implementations.  Modules that cannot be
     imported (e.g. the trainer without ``accelerate``) are skipped.  Returns the list patched."""
     done = []
@@ -78,6 +84,16 @@ def install(loss_module="utils.loss_func", trainer_module="utils.trainer_v3_g",
         am.MaskedPooling.forward = _masked_forward
         am.MaskAdapterPooling.forward = _adapter_forward
         done.append(am.__name__)
+    bm = (_maybe(branch_module) if isinstance(branch_module, str) else branch_module) if head else None
+    if bm is not None and hasattr(bm, "SupportBranch"):
+        _saved.setdefault((bm.__name__, "SupportBranch.forward"), bm.SupportBranch.forward)
+        bm.SupportBranch.forward = _sh.support_branch_forward
+        done.append(bm.__name__)
+    dm = (_maybe(decoder_module) if isinstance(decoder_module, str) else decoder_module) if decoder else None
+    if dm is not None and hasattr(dm, "MaskDecoder"):
+        _saved.setdefault((dm.__name__, "MaskDecoder.predict_masks"), dm.MaskDecoder.predict_masks)
+        dm.MaskDecoder.predict_masks = _md.predict_masks
+        done.append(dm.__name__)
     return done
 
 

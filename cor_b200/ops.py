@@ -30,7 +30,8 @@ _KERNELS_PER_CALL = {
     "cor_mask_prep": 2, "cor_pool_stream_fwd": 1, "cor_pool_umma_fwd": 1, "cor_rows_finalize": 1,
     "cor_rows_finalize_bwd": 1, "cor_pool_bwd_feat": 1, "cor_pool_bwd_umma": 1, "cor_pool_bwd_maps": 1, "cor_fgbg_loss_fwd": 2,
     "cor_fgbg_loss_bwd": 1, "cor_step_combine": 1, "cor_seg_loss_fwd": 2, "cor_seg_loss_bwd": 1, "cor_sim_stream_fwd": 2,
-    "cor_sim_umma_fwd": 2, "cor_infonce_coef": 1, "cor_sim_umma_coef": 1, "cor_infonce_bwd_umma": 3, "cor_sim_lse_parts": 1, "cor_infonce_tail": 1, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
+    "cor_sim_umma_fwd": 2, "cor_infonce_coef": 1, "cor_sim_umma_coef": 1, "cor_infonce_bwd_umma": 3, "cor_gemm_bf16": 1, "cor_cast_cat_bf16": 1, "cor_act_bwd": 1,
+    "cor_hyper_logits_fwd": 1, "cor_hyper_logits_bwd": 2, "cor_sim_lse_parts": 1, "cor_infonce_tail": 1, "cor_infonce_fwd": 1, "cor_infonce_bwd": 2, "cor_topk": 1, "cor_l2_normalize": 1,
     "cor_val_post": 3, "cor_soft_metrics": 2,
 }
 
@@ -486,7 +487,14 @@ def _sim_lse_parts(r16, q16, inv_tau, engine):
 
 
 def _to_bf16_rows(x: torch.Tensor) -> torch.Tensor:
-    return x.reshape(-1, x.shape[-1]).to(torch.bfloat16).contiguous()
+    """[.., D] -> bf16 [rows, D] on our own cast kernel (fp32 input) -- not an ATen copy."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.dtype == torch.bfloat16:
+        return x2.contiguous()
+    x2 = x2.float().contiguous()
+    out = torch.empty(x2.shape, dtype=torch.bfloat16, device=x2.device)
+    _call("cor_cast_cat_bf16", x2.device, ptr(x2), x2.shape[1], None, 0, _ll(x2.shape[0]), ptr(out))
+    return out
 
 
 def similarity(regions: torch.Tensor, queries: torch.Tensor, engine: str = "auto") -> torch.Tensor:

@@ -156,7 +156,7 @@ class _FusedStepFn(torch.autograd.Function):
         q16 = torch.empty((B, comb_c.shape[1]), dtype=torch.bfloat16, device=dev)
         ev_q = None
         with torch.cuda.stream(side if side is not None else cur):
-            q16.copy_(comb_c)                # bf16 queries for the similarity stage, off the main chain
+            call("cor_cast_cat_bf16", dev, ptr(comb_c), comb_c.shape[1], None, 0, _ll(B), ptr(q16))   # bf16 queries, off the main chain
             if side is not None:
                 ev_q = torch.cuda.Event()
                 ev_q.record(side)

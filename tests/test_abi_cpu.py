@@ -142,6 +142,12 @@ def test_hooks_install_into_the_real_reference():
             sb.SupportBranch("ViT-B-16-SigLIP-384", "unused", mask_pooling="nope")
         assert type(sb.SupportBranch("ViT-B-16-SigLIP-384", "unused", mask_pooling="MaskedPooling").mask_pooling).forward \
             is hooks._masked_forward
+        # the composed-query head and the decoder's hypernetwork product are rebound on the reference's own classes too
+        from cor_b200 import mask_decoder as md, support_head as sh
+        import lib.sam_model.mask_decoder as ref_md
+        assert sb.SupportBranch.forward is sh.support_branch_forward
+        assert ref_md.MaskDecoder.predict_masks is md.predict_masks
+        assert "lib.support_branch" in done and "lib.sam_model.mask_decoder" in done
     finally:
         hooks.uninstall()
     assert ref_lf.wbce_with_wiou_loss is orig
@@ -165,6 +171,11 @@ def test_argument_validation_fails_before_any_launch(lib):
         ("cor_infonce_coef", (one, one, one, 0, 8, 1.0, one, 1.0, one, null)),           # no queries
         ("cor_sim_lse_parts", (0, one, one, 8, 4, 64, 1.0, one, None, None, null)),      # nowhere to report the layout
         ("cor_topk", (one, one, one, 8, 4, 64, 9, one, one, null)),                      # k > Nr
+        ("cor_gemm_bf16", (one, 0, 8, 0, one, 0, 8, 0, 8, 8, 0, 1, 1.0, null, 0, null, null, null, 0, 8, one, 0, 8, null, 0, null, null)),  # K = 0
+        ("cor_gemm_bf16", (one, 0, 8, 0, one, 0, 8, 0, 8, 8, 64, 1, 1.0, null, 9, null, null, null, 0, 8, one, 0, 8, null, 0, null, null)), # unknown activation
+        ("cor_hyper_logits_fwd", (one, one, 0, one, 0, 2, 4, 0, 5, 32, 64, null)),       # more tokens than exist
+        ("cor_infonce_bwd_umma", (one, one, 64, 64, 100, 1.0, one, one, one, 1.0, one, one, one, null)),   # D not a multiple of 64
+        ("cor_act_bwd", (one, null, null, null, 1, 4, 4, one, null, null)),              # relu without the activation output
     ]
     for name, args in cases:
         rc = getattr(lib, name)(*args)
