@@ -677,11 +677,15 @@ def main():
     barrier()
     t0 = time.perf_counter()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(e2e_steps + 1)]
     s0.record()
-    for _ in range(e2e_steps):
+    marks[0].record()
+    for i in range(e2e_steps):
         bufs.run(host, **kw)
+        marks[i + 1].record()
     s1.record()
     barrier()
+    per_step = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(e2e_steps)]      # diagnosis only: the value is the mean
     # how much of a step is the copy: the same loads alone, events around them (max over ranks)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
@@ -762,7 +766,7 @@ def main():
                         "numa_how": numa["how"], "pcie_gbs_per_gpu": pcie_all,
                         "pcie_note": "8 back-to-back pinned cudaMemcpyAsync H2D copies of 1 GiB on every GPU at once, timed as one interval: the "
                                      "sustained platform ceiling of this leg (GPUs that share a PCIe uplink halve each other)",
-                        "h2d_ms_per_step": h2d_ms, "frac_of_pcie_bound": (bufs.h2d_bytes / (min(pcie_all) * 1e9) * 1e3) / float(e2e_ms),
+                        "h2d_ms_per_step": h2d_ms, "per_step_ms_rank0": per_step, "frac_of_pcie_bound": (bufs.h2d_bytes / (min(pcie_all) * 1e9) * 1e3) / float(e2e_ms),
                         "pcie_bound_ms_per_step": bufs.h2d_bytes / (min(pcie_all) * 1e9) * 1e3},
                 "gpu_launches": launches, "graphed": graphed, "roofline": roofline, "secondary_kernels": secondary, "variants": variants,
                 "kernel_ms_per_step": {k: round(v, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])},

@@ -63,7 +63,7 @@ for B in [int(b) for b in args.batches.split(",")]:
         alg = B * 256 * 256 * (2 + taps * esz)
         sect = B * 256 * 256 * 2 + (mask.numel() * esz // (2 if taps == 4 else 1))
         for strip in (1, 0):
-            os.environ["COR_SEG_STRIP"] = str(strip)
+            os.environ["COR_SEG_STRIP"] = "2" if strip else "0"
             t_f = timed(lambda: ops.seg_loss(pred, mask))
             pg = pred.detach().requires_grad_(True)
             t_fb = timed(lambda: ops.seg_loss(pg, mask).backward())

@@ -16,6 +16,8 @@
 // prefixes -- one named barrier per kSG rows.  Per-pixel terms accumulate in registers; one fixed-order block
 // reduction per CTA at the end (deterministic).
 // Warp roles (288 threads): 0..7 consumers (column = threadIdx.x), 8 = TMA producer.
+#include <stdlib.h>
+
 #include "seg_common.cuh"
 #include "umma.cuh"
 
@@ -293,6 +295,13 @@ int seg_strip_try_launch(const void* pred, int pred_dtype, const void* mask, int
   const int ep = pred_dtype == COR_F32 ? 4 : 2;
   // shapes the strip kernel serves; everything else (other ratios, wide or oddly pitched images) takes the tile kernel
   if (!(same || four) || W > kSW || W % 16 != 0) return COR_EINVAL;
+  // a handful of samples with 2/4-byte 4x masks: too few strips to hide each CTA's serial row chain -- the 64x64 tile kernel
+  // measures faster there (B=16, 1024^2 fp32 -> 256^2: 32.8 vs 38.9 us; B=128: 147 vs 111 us).  COR_SEG_STRIP=2 forces strips.
+  {
+    const char* knob = getenv("COR_SEG_STRIP");
+    const bool force = knob && atoi(knob) == 2;
+    if (!force && four && em >= 2 && (long long)N * H * W < (1ll << 21)) return COR_EINVAL;
+  }
   if (((uintptr_t)mask & 15) || ((uintptr_t)pred & 15) || (ns * em) % 16 != 0 || ((long long)Wm * em) % 16 != 0 || ((long long)W * ep) % 16 != 0)
     return COR_EINVAL;
 #define COR_STRIP(TP, TM) return strip_launch<TP, TM>(pred, mask, mscale, N, H, W, Hm, Wm, ns, fa, fg_, t_save, w_save, part, strips, st)

@@ -41,7 +41,10 @@ def _masked_forward(self, clip_feature, mask):
 def _adapter_forward(self, clip_feature, mask):
     if mask.shape[-2:] != clip_feature.shape[-2:]:
         mask = F.interpolate(mask, size=clip_feature.shape[-2:], mode="bilinear", align_corners=False)
-    maps = self.get_mask_map(self.channel_clip_to_maskadapter(clip_feature), mask)
+    if _ma._adapter_maps_ok(clip_feature):
+        maps = _ma.adapter_maps(self, clip_feature, mask)        # the reference module's own parameters, our kernels
+    else:
+        maps = self.get_mask_map(self.channel_clip_to_maskadapter(clip_feature), mask)
     return _ma.softmax_map_pool_tail(maps, clip_feature, self.num_output_maps)
 
 

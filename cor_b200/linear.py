@@ -17,7 +17,7 @@ from . import _lib as L
 from . import ops
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CorError
 
-__all__ = ["gemm", "linear", "cast_bf16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_SIGMOID"]
+__all__ = ["gemm", "linear", "ln_rows", "cast_bf16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_SIGMOID"]
 
 _ACTS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "sigmoid": ACT_SIGMOID}
 
@@ -65,61 +65,114 @@ _w16_cache = {}
 
 
 def _weight_bf16(w: torch.Tensor) -> torch.Tensor:
-    """bf16 copy of a parameter, refreshed when the parameter is updated in place (optimizer step bumps ``_version``)."""
-    key = (w.data_ptr(), tuple(w.shape))
+    """bf16 copy of a weight.  Cached only for parameters (or views of parameters, e.g. ``conv.weight.view(out, in)``):
+    keyed on the parameter object (weak reference) and its ``_version``, which an optimizer's in-place update bumps.
+    Computed weights (e.g. a product of two parameters) are cast on every call."""
+    import weakref
+    base = w._base if w._base is not None else w
+    if not isinstance(base, torch.nn.Parameter):
+        return cast_bf16(w.detach().reshape(w.shape[0], -1))
+    key = (id(base), tuple(w.shape), w.storage_offset())
     hit = _w16_cache.get(key)
-    if hit is not None and hit[0] == w._version:
-        return hit[1]
+    if hit is not None and hit[0]() is base and hit[1] == base._version:
+        return hit[2]
     w16 = cast_bf16(w.detach().reshape(w.shape[0], -1))
-    _w16_cache[key] = (w._version, w16)
+    _w16_cache[key] = (weakref.ref(base), base._version, w16)
     return w16
 
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, drop_mask, x2):
-        dev = L.require_cuda(x, weight, bias, drop_mask, x2)
+    def forward(ctx, x, weight, bias, act, drop_mask, x2, colscale, residual):
+        dev = L.require_cuda(x, weight, bias, drop_mask, x2, colscale, residual)
         rows = x.shape[0]
-        x16 = cast_bf16(x, x2)                       # [rows, K]; torch.cat((x, x2), -1) fused with the cast
+        x16 = cast_bf16(x, x2) if x.dtype != torch.bfloat16 or x2 is not None else x.contiguous()   # torch.cat((x, x2), -1) fused with the cast
         w16 = _weight_bf16(weight)
         N, K = w16.shape
         if x16.shape[1] != K:
             raise CorError(f"linear: input width {x16.shape[1]} != weight in_features {K}")
+        if colscale is not None and act != ACT_NONE:
+            raise CorError("linear: a column scale goes with no activation (ConvNeXt's gamma * pwconv2(.))")
         b32 = bias.float().contiguous() if bias is not None else None
         m32 = drop_mask.float().contiguous() if drop_mask is not None else None
-        y, pre = gemm(x16, w16, rows, N, K, bias=b32, act=act, emul=m32, want_pre=True) if act == ACT_GELU else \
-            (gemm(x16, w16, rows, N, K, bias=b32, act=act, emul=m32), None)
-        ctx.save_for_backward(x16, w16, y, pre, m32)
+        cs = colscale.float().contiguous() if colscale is not None else None
+        want_pre = act == ACT_GELU or (cs is not None and colscale.requires_grad)
+        out = gemm(x16, w16, rows, N, K, bias=b32, act=act, emul=m32, colscale=cs, residual=residual, want_pre=want_pre)
+        y, pre = out if want_pre else (out, None)
+        # relu / sigmoid differentiate through the stored OUTPUT (only used when there is neither scale nor residual)
+        ctx.save_for_backward(x16, w16, y if act in (ACT_RELU, ACT_SIGMOID) else None, pre, m32, cs)
         ctx.cfg = (act, x.shape[1], x.requires_grad, x2 is not None and x2.requires_grad, weight.requires_grad,
-                   bias is not None and bias.requires_grad, x.dtype, weight.dtype, tuple(weight.shape))
+                   bias is not None and bias.requires_grad, colscale is not None and colscale.requires_grad,
+                   residual is not None and residual.requires_grad, x.dtype, weight.dtype, tuple(weight.shape), rows, N)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x16, w16, y, pre, m32 = ctx.saved_tensors
-        act, c0, need_x, need_x2, need_w, need_b, xdt, wdt, wshape = ctx.cfg
-        dev = y.device
-        rows, N = y.shape
+        x16, w16, y, pre, m32, cs = ctx.saved_tensors
+        act, c0, need_x, need_x2, need_w, need_b, need_cs, need_res, xdt, wdt, wshape, rows, N = ctx.cfg
+        dev = x16.device
         K = x16.shape[1]
         gy = gy.float().contiguous()
         dz = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
         db = torch.empty((N,), dtype=torch.float32, device=dev) if need_b else None
-        # relu / sigmoid differentiate through the stored OUTPUT: with a dropout mask folded in, y = mask * act(z), and
-        # y > 0 <=> act(z) > 0 on kept elements (dropped ones get zero gradient from the mask factor anyway); sigmoid is
-        # never combined with a mask in the reference
-        ops._call("cor_act_bwd", dev, ops.ptr(gy), ops.ptr(y), ops.ptr(pre), ops.ptr(m32), int(act), rows, N, ops.ptr(dz), ops.ptr(db))
+        dcs = torch.empty((N,), dtype=torch.float32, device=dev) if need_cs else None
+        work = ops._work(L.load().cor_act_bwd_work_bytes(rows, N), dev) if (need_b or need_cs) else None
+        ops._call("cor_act_bwd", dev, ops.ptr(gy), ops.ptr(y), ops.ptr(pre), ops.ptr(m32), ops.ptr(cs), int(act), ops._ll(rows), N,
+                  ops.ptr(dz), ops.ptr(db), ops.ptr(dcs), ops.ptr(work))
         gx = gx2 = gw = None
         if need_x or need_x2:
             g_in = gemm(dz, w16, rows, K, N, b_mn=True)                   # dX = dZ W : W [N, K] read as the MN-major B (k = out features)
-            gx = g_in[:, :c0].to(xdt) if need_x else None
+            gx = (g_in[:, :c0] if c0 != K else g_in).to(xdt) if need_x else None
             gx2 = g_in[:, c0:].to(xdt) if need_x2 else None
         if need_w:
             gw = gemm(dz, x16, N, K, rows, a_mn=True, b_mn=True).view(wshape).to(wdt)   # dW = dZ^T X : both operands MN-major (k = rows)
-        return gx, gw, db, None, None, gx2
+        return gx, gw, db, None, None, gx2, dcs, (gy if need_res else None)
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
-           drop_mask: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``drop_mask * act(cat(x, x2) @ weight.T + bias)`` -> f32 [rows, out_features]; x [rows, in] (any leading shape is
-    flattened by the caller).  ``drop_mask`` holds 0 or 1/(1-p) per element (what ``F.dropout`` multiplies by)."""
-    return _LinearFn.apply(x, weight, bias, _ACTS[act], drop_mask, x2)
+           drop_mask: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None, colscale: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``residual + colscale * drop_mask * act(cat(x, x2) @ weight.T + bias)`` -> f32 [rows, out_features]; x [rows, in] f32
+    or bf16 (any leading shape is flattened by the caller).  ``drop_mask`` holds 0 or 1/(1-p) per element (what
+    ``F.dropout`` multiplies by); ``colscale`` [out] and ``residual`` [rows, out] are ConvNeXt's layer scale and skip
+    connection (mask_adapter.py:215-221), fused into the same GEMM epilogue."""
+    return _LinearFn.apply(x, weight, bias, _ACTS[act], drop_mask, x2, colscale, residual)
+
+
+class _LnRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, act, out_bf16):
+        dev = L.require_cuda(x, weight, bias)
+        x = x.float().contiguous()
+        rows, Cc = x.shape
+        w, b = weight.float().contiguous(), bias.float().contiguous()
+        y = torch.empty((rows, Cc), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=dev)
+        ops._call("cor_ln_rows_fwd", dev, ops.ptr(x), ops.ptr(w), ops.ptr(b), ops._ll(rows), Cc, ops._f(eps), int(act), ops.ptr(y),
+                  L.dtype_code(y), ops.ptr(stats))
+        ctx.save_for_backward(x, w, b, stats)
+        ctx.cfg = (int(act), weight.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, b, stats = ctx.saved_tensors
+        act, wdt = ctx.cfg
+        dev = x.device
+        rows, Cc = x.shape
+        gy = gy.float().contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        db = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        work = ops._work(L.load().cor_ln_rows_work_bytes(rows, Cc), dev)
+        ops._call("cor_ln_rows_bwd", dev, ops.ptr(gy), ops.ptr(x), ops.ptr(w), ops.ptr(b), ops.ptr(stats), ops._ll(rows), Cc, act, ops.ptr(dx),
+                  ops.ptr(dw), ops.ptr(db), ops.ptr(work))
+        return dx, dw.to(wdt), db.to(wdt), None, None, None
+
+
+def ln_rows(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6, act: Optional[str] = None,
+            out_bf16: bool = False) -> torch.Tensor:
+    """Row-wise LayerNorm over the last axis of x [rows, C] (+ optional GELU), biased variance -- both data formats of the
+    reference's LayerNorm (mask_adapter.py:226-251) once the tensor is laid out channels-last.  ``out_bf16`` writes the next
+    GEMM's A operand directly."""
+    return _LnRowsFn.apply(x, weight, bias, float(eps), _ACTS[act], bool(out_bf16))

@@ -3,8 +3,18 @@
 ``MaskedPooling`` and ``MaskAdapterPooling`` keep the reference's constructor arguments, forward
 signatures, output shapes and PARAMETER NAMES (``channel_clip_to_maskadapter.*``, ``get_mask_map.*``),
 so checkpoints written by the reference load with ``strict=True`` (my_test.py:145).  The pooling
-tails (mask_adapter.py:19-24 and :62-79) run in libcor_b200.so; the learned map generator is dense
-conv / linear work and stays on cuDNN / cuBLAS.
+tails (mask_adapter.py:19-24 and :62-79) run in libcor_b200.so.
+
+The learned half (``ChannelReduction`` :83-94 and ``GenerateMaskAdapterMap`` :97-179) runs through
+:func:`adapter_maps` on CUDA: channels-last rows end to end, every 1x1 convolution / ``nn.Linear`` (channel reduction,
+``fuse``, the 4x point-wise MLP of the three ConvNeXt blocks with GELU, layer scale and the skip connection in the GEMM
+epilogue, the final 8-map head) forward AND backward on the tcgen05 GEMM (``cor_gemm_bf16``), every LayerNorm (+GELU) on
+``cor_ln_rows_fwd/bwd``.  The reference adds the mask feature to a feature map REPEATED once per mask and then applies
+``fuse`` (:155-163); a 1x1 convolution is linear, so ``fuse(x + m) = fuse(x) + fuse_w m``: the feature half is computed
+once per IMAGE and the mask half by a [256 x 16] matrix composed from ``fuse`` and the last mask-downscaling conv --
+the Q-fold repeat and the [B Q, 512, h, w] mask feature never exist.  What stays on cuDNN: the two tiny stride-2 3x3
+convolutions of ``mask_downscaling`` (1 -> 4 -> 16 channels) and the depth-wise 7x7 convolutions (channels-last, no copy).
+The module classes below keep the reference's eager definition as their CPU-importable form and parameter container.
 """
 from __future__ import annotations
 
@@ -14,7 +24,7 @@ import torch.nn.functional as F
 
 from . import ops
 
-__all__ = ["MaskedPooling", "MaskAdapterPooling", "masked_pool_tail", "softmax_map_pool_tail"]
+__all__ = ["MaskedPooling", "MaskAdapterPooling", "masked_pool_tail", "softmax_map_pool_tail", "adapter_maps"]
 
 
 def masked_pool_tail(clip_feature: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
@@ -111,6 +121,61 @@ class GenerateMaskAdapterMap(nn.Module):
         return x.reshape(B, Q * x.shape[1], H, W)
 
 
+def _rows(x_nchw: torch.Tensor) -> torch.Tensor:
+    """[N,C,h,w] -> channels-last rows [N*h*w, C] (a view when the tensor already is channels_last)."""
+    n, c, h, w = x_nchw.shape
+    return x_nchw.permute(0, 2, 3, 1).reshape(n * h * w, c)
+
+
+def _convnext_rows(blk, y: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    """One ConvNeXt block (mask_adapter.py:182-223) on channels-last rows y [n*h*w, C] (f32)."""
+    from .linear import linear, ln_rows
+    c = y.shape[1]
+    img = y.view(n, h, w, c).permute(0, 3, 1, 2)                       # NCHW shape, channels_last strides: no copy
+    t = F.conv2d(img, blk.dwconv.weight.float(), blk.dwconv.bias.float(), padding=blk.dwconv.padding, groups=c)
+    t = ln_rows(_rows(t), blk.norm.weight, blk.norm.bias, blk.norm.eps, None, out_bf16=True)
+    hdn = linear(t, blk.pwconv1.weight, blk.pwconv1.bias, "gelu")
+    # gamma * pwconv2(.) + input: layer scale and skip connection in the GEMM epilogue
+    return linear(hdn, blk.pwconv2.weight, blk.pwconv2.bias, None, None, None, blk.gamma, y)
+
+
+def adapter_maps(adapter, clip_feature: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """``get_mask_map(channel_clip_to_maskadapter(clip_feature), mask)`` (mask_adapter.py:59-60) with ``adapter``'s own
+    parameters: clip_feature [B,C,h,w], mask [B,Q,h,w] (already at the feature resolution) -> maps [B, Q*num_output_maps, h, w]."""
+    from .linear import linear, ln_rows
+    cr, gm = adapter.channel_clip_to_maskadapter, adapter.get_mask_map
+    B, C, h, w = clip_feature.shape
+    Q = mask.shape[1]
+    P = h * w
+    # ChannelReduction (:83-94): 1x1 conv -> LayerNorm(channels_first) -> GELU, on channels-last rows
+    x = linear(_rows(clip_feature.float()), cr.conv.weight.view(cr.conv.out_channels, C), cr.conv.bias)
+    x = ln_rows(x, cr.norm.weight, cr.norm.bias, cr.norm.eps, "gelu")                                     # [B*P, 512]
+    # mask branch (:157-158): x4 bilinear up, two stride-2 3x3 convs with LN + GELU -> 16 channels at h x w (tiny; cuDNN)
+    md = gm.mask_downscaling
+    m = F.interpolate(mask.reshape(B * Q, 1, h, w).float(), size=(4 * h, 4 * w), mode="bilinear", align_corners=False)
+    m16 = md[5](md[4](md[3](md[2](md[1](md[0](m))))))                                                    # [B*Q, 16, h, w]
+    # fuse(x + conv(m16)) = fuse(x) + (fuse_w conv_w) m16 + fuse_w conv_b + fuse_b   (:161-163; 1x1 convs are linear)
+    mid = gm.fuse.out_channels
+    fuse_w = gm.fuse.weight.view(mid, -1).float()
+    conv_w = md[6].weight.view(md[6].out_channels, -1).float()
+    w_comp = fuse_w @ conv_w                                                                              # [256, 16]
+    b_comp = fuse_w @ md[6].bias.float() + gm.fuse.bias.float()
+    fx = linear(x, gm.fuse.weight.view(mid, -1), None)                                                    # once per image: [B*P, 256]
+    fm = linear(_rows(m16), w_comp, b_comp)                                                               # [B*Q*P, 256]
+    y = (fm.view(B, Q, P, mid) + fx.view(B, 1, P, mid)).reshape(B * Q * P, mid)
+    for blk in (gm.cnext1, gm.cnext2, gm.cnext3):
+        y = _convnext_rows(blk, y, B * Q, h, w)
+    y = ln_rows(y, gm.norm.weight, gm.norm.bias, gm.norm.eps, None, out_bf16=True)
+    nmaps = gm.final.out_channels
+    o = linear(y, gm.final.weight.view(nmaps, mid), gm.final.bias)                                        # [B*Q*P, 8]
+    return o.view(B, Q, P, nmaps).permute(0, 1, 3, 2).reshape(B, Q * nmaps, h, w)
+
+
+def _adapter_maps_ok(clip_feature: torch.Tensor) -> bool:
+    """Shapes the GEMM path takes: CUDA, channel counts that give 16-byte TMA row pitches (all of the reference's)."""
+    return clip_feature.is_cuda and clip_feature.shape[1] % 8 == 0
+
+
 class MaskAdapterPooling(nn.Module):
     def __init__(self, x_in_channel=1152, mask_adatpet_network_in_channel=256, mask_downscaling_mid_channel=16,
                  mask_adatpet_network_mid_channel=256, num_output_maps=16):
@@ -123,5 +188,8 @@ class MaskAdapterPooling(nn.Module):
     def forward(self, clip_feature: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         if mask.shape[-2:] != clip_feature.shape[-2:]:
             mask = F.interpolate(mask, size=clip_feature.shape[-2:], mode="bilinear", align_corners=False)
-        maps = self.get_mask_map(self.channel_clip_to_maskadapter(clip_feature), mask)
+        if _adapter_maps_ok(clip_feature):
+            maps = adapter_maps(self, clip_feature, mask)
+        else:   # CPU import / odd channel counts: the eager definition (the pooling tail below still refuses CPU tensors)
+            maps = self.get_mask_map(self.channel_clip_to_maskadapter(clip_feature), mask)
         return softmax_map_pool_tail(maps, clip_feature, self.num_output_maps)

@@ -164,7 +164,8 @@ int cor_step_combine(const float* seg, const float* fgbg, const float* nce, floa
  *   per_sample [N, cor_seg_loss_npartials()] partial sums saved for backward;
  *   t_save, w_save [N,H,W] f32 (resampled target, edge weight) or NULL when no backward is needed.
  *   Kernels: a TMA-streamed row-strip kernel when the mask is at the logit size or at exactly 4x it (W <= 256,
- *   W % 16 == 0, 16-byte aligned), a 64x64 tile kernel otherwise (COR_SEG_STRIP=0 forces the latter).
+ *   W % 16 == 0, 16-byte aligned), a 64x64 tile kernel otherwise -- and for small batches of 2/4-byte 4x masks, where it measures
+ *   faster (COR_SEG_STRIP=0 forces the tile kernel, =2 the strip kernel wherever it applies).
  * ---------------------------------------------------------------------------------------- */
 enum { COR_SEG_WBCE = 0, COR_SEG_WIOU = 1, COR_SEG_DICE = 2, COR_SEG_BCE = 3, COR_SEG_IOU = 4, COR_SEG_WDICE = 5, COR_SEG_FOCAL = 6,
        COR_SEG_NTERMS = 7 };
@@ -283,11 +284,24 @@ int cor_gemm_bf16(const void* A, int a_mn, long long a_rows_total, long long a_b
 /* Operand prep and epilogue backward for cor_gemm_bf16 (csrc/ew.cu).
  *   cor_cast_cat_bf16: out[r] = bf16(concat(a[r][0:c0], b[r][0:c1])) (b NULL, c1 = 0: a plain cast) -- torch.cat at
  *                      cir_feature_fuse.py:49,54 fused with the operand cast.
- *   cor_act_bwd: dz = dy * emul * act'(.) as bf16 [M,N] and db[n] = sum_m dz (rows in order).  y_f32 = activation output
- *                before the dropout mask (relu, sigmoid), pre_bf16 = pre-activation saved by the GEMM (gelu). */
+ *   cor_act_bwd: dz = dy * emul * colscale * act'(.) as bf16 [M,N]; db[n] = sum_m dz; dcolscale[n] = sum_m dy * emul * pre
+ *                (rows in chunk order: deterministic).  y_f32 = activation output before mask / scale (relu, sigmoid),
+ *                pre_bf16 = pre-activation saved by the GEMM (gelu; the un-scaled linear output for a column scale).
+ *                work: cor_act_bwd_work_bytes(M, N) bytes when db or dcolscale is requested. */
 int cor_cast_cat_bf16(const float* a, int c0, const float* b, int c1, long long rows, void* out_bf16, cor_stream_t stream);
-int cor_act_bwd(const float* dy, const float* y_f32, const void* pre_bf16, const float* emul, int act, int M, int N,
-                void* dz_bf16, float* db, cor_stream_t stream);
+size_t cor_act_bwd_work_bytes(long long M, int N);
+int cor_act_bwd(const float* dy, const float* y_f32, const void* pre_bf16, const float* emul, const float* colscale, int act,
+                long long M, int N, void* dz_bf16, float* db, float* dcolscale, void* work, cor_stream_t stream);
+
+/* Row-wise LayerNorm (+ optional GELU) over channels-last rows, forward and backward (csrc/ln_rows.cu): the norms of the
+ * MaskAdapter map generator (lib/support_model/mask_adapter.py:83-94, :171-173, :200-209, :240-251).
+ *   y = act((x - mean) * rstd * weight + bias), x [rows, C] f32, C <= 1024; y f32 or bf16; stats [rows, 2] = {mean, rstd}.
+ *   bwd: dx [rows, C], dweight / dbias [C]; work: cor_ln_rows_work_bytes(rows, C). */
+size_t cor_ln_rows_work_bytes(long long rows, int C);
+int cor_ln_rows_fwd(const float* x, const float* weight, const float* bias, long long rows, int C, float eps, int act,
+                    void* y, int y_dtype, float* stats, cor_stream_t stream);
+int cor_ln_rows_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* stats,
+                    long long rows, int C, int act, float* dx, float* dweight, float* dbias, void* work, cor_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Mask-logit producer: the hypernetwork product of the SAM decoder,

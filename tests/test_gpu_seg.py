@@ -33,7 +33,7 @@ def _inputs(seed, N, H, W, scale, mask_dtype, pred_dtype=torch.bfloat16, soft=Tr
 
 def _run(pred, mask, strip, **kw):
     from cor_b200 import ops
-    os.environ["COR_SEG_STRIP"] = "1" if strip else "0"
+    os.environ["COR_SEG_STRIP"] = "2" if strip else "0"
     try:
         p = pred.to(dev()).requires_grad_(True)
         loss, extra = ops.seg_loss(p, mask.to(dev()), return_extras=True, **kw)
@@ -84,7 +84,7 @@ def test_class_n_variants_forward_backward(name, strip):
     from cor_b200 import loss_func as lf
     from oracle import aten_port as ap
     pred, mask = _inputs(29, 4, 96, 64, 1, torch.float32, torch.float32)
-    os.environ["COR_SEG_STRIP"] = "1" if strip else "0"
+    os.environ["COR_SEG_STRIP"] = "2" if strip else "0"
     try:
         p = pred.to(dev()).requires_grad_(True)
         v = getattr(lf, name)(p, mask.to(dev()))
