@@ -685,6 +685,7 @@ def main():
         marks[i + 1].record()
     s1.record()
     barrier()
+    wall = (time.perf_counter() - t0) / e2e_steps
     per_step = [round(marks[i].elapsed_time(marks[i + 1]), 2) for i in range(e2e_steps)]      # diagnosis only: the value is the mean
     # how much of a step is the copy: the same loads alone, events around them (max over ranks)
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -697,7 +698,6 @@ def main():
     if world > 1:
         dist.all_reduce(h2d_t, op=dist.ReduceOp.MAX)
     h2d_ms = float(h2d_t)
-    wall = (time.perf_counter() - t0) / e2e_steps
     e2e_ms = torch.tensor([max(s0.elapsed_time(s1) / e2e_steps, wall * 1e3)], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)

@@ -17,7 +17,7 @@ from . import _lib as L
 from . import ops
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CorError
 
-__all__ = ["gemm", "linear", "ln_rows", "cast_bf16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_SIGMOID"]
+__all__ = ["gemm", "linear", "ln_rows", "dwconv7_rows", "cast_bf16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_SIGMOID"]
 
 _ACTS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "sigmoid": ACT_SIGMOID}
 
@@ -176,3 +176,48 @@ def ln_rows(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: floa
     reference's LayerNorm (mask_adapter.py:226-251) once the tensor is laid out channels-last.  ``out_bf16`` writes the next
     GEMM's A operand directly."""
     return _LnRowsFn.apply(x, weight, bias, float(eps), _ACTS[act], bool(out_bf16))
+
+
+class _DwConv7Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_rows, weight, bias, n, h, w):
+        dev = L.require_cuda(x_rows, weight, bias)
+        x = x_rows.float().contiguous()
+        Cc = x.shape[1]
+        wt = weight.float().reshape(Cc, 49).contiguous()
+        b = bias.float().contiguous() if bias is not None else None
+        out = torch.empty_like(x)
+        ops._call("cor_dwconv7_cl", dev, ops.ptr(x), ops.ptr(wt), ops.ptr(b), ops.ptr(out), n, h, w, Cc, 0)
+        ctx.save_for_backward(x, wt)
+        ctx.cfg = (n, h, w, weight.dtype, tuple(weight.shape), bias is not None, x_rows.requires_grad, weight.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wt = ctx.saved_tensors
+        n, h, w, wdt, wshape, has_b, need_x, need_w = ctx.cfg
+        dev = x.device
+        Cc = x.shape[1]
+        gy = gy.float().contiguous()
+        gx = gw = gb = None
+        if need_x:
+            gx = torch.empty_like(x)
+            ops._call("cor_dwconv7_cl", dev, ops.ptr(gy), ops.ptr(wt), None, ops.ptr(gx), n, h, w, Cc, 1)       # flipped kernel
+        if need_w or has_b:
+            gw32 = torch.empty((Cc, 49), dtype=torch.float32, device=dev)
+            gb32 = torch.empty((Cc,), dtype=torch.float32, device=dev) if has_b else None
+            work = ops._work(L.load().cor_dwconv7_work_bytes(n, h, w, Cc), dev)
+            ops._call("cor_dwconv7_cl_wgrad", dev, ops.ptr(x), ops.ptr(gy), ops.ptr(gw32), ops.ptr(gb32), n, h, w, Cc, ops.ptr(work))
+            gw = gw32.view(wshape).to(wdt)
+            gb = gb32.to(wdt) if has_b else None
+        return gx, gw, gb, None, None, None
+
+
+def dwconv7_rows(x_rows: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], n: int, h: int, w: int) -> torch.Tensor:
+    """Depth-wise 7x7 convolution (padding 3) of n maps given as channels-last rows [n*h*w, C] -> rows of the same shape:
+    ``nn.Conv2d(C, C, 7, padding=3, groups=C)`` (mask_adapter.py:196-199) without leaving the rows layout."""
+    return _DwConv7Fn.apply(x_rows, weight, bias, int(n), int(h), int(w))
+
+
+def dwconv7_ok(Cc: int, h: int, w: int) -> bool:
+    return Cc % 32 == 0 and (w + 6) * 7 * 32 * 4 * 2 <= 200 * 1024

@@ -12,8 +12,9 @@ epilogue, the final 8-map head) forward AND backward on the tcgen05 GEMM (``cor_
 ``cor_ln_rows_fwd/bwd``.  The reference adds the mask feature to a feature map REPEATED once per mask and then applies
 ``fuse`` (:155-163); a 1x1 convolution is linear, so ``fuse(x + m) = fuse(x) + fuse_w m``: the feature half is computed
 once per IMAGE and the mask half by a [256 x 16] matrix composed from ``fuse`` and the last mask-downscaling conv --
-the Q-fold repeat and the [B Q, 512, h, w] mask feature never exist.  What stays on cuDNN: the two tiny stride-2 3x3
-convolutions of ``mask_downscaling`` (1 -> 4 -> 16 channels) and the depth-wise 7x7 convolutions (channels-last, no copy).
+the Q-fold repeat and the [B Q, 512, h, w] mask feature never exist.  The depth-wise 7x7 convolutions run on
+``cor_dwconv7_cl`` (channels-last, forward, input gradient = flipped kernel, weight gradient).  What stays on cuDNN: the two
+tiny stride-2 3x3 convolutions of ``mask_downscaling`` (1 -> 4 -> 16 channels, with their LayerNorm + GELU).
 The module classes below keep the reference's eager definition as their CPU-importable form and parameter container.
 """
 from __future__ import annotations
@@ -129,11 +130,14 @@ def _rows(x_nchw: torch.Tensor) -> torch.Tensor:
 
 def _convnext_rows(blk, y: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
     """One ConvNeXt block (mask_adapter.py:182-223) on channels-last rows y [n*h*w, C] (f32)."""
-    from .linear import linear, ln_rows
+    from .linear import dwconv7_ok, dwconv7_rows, linear, ln_rows
     c = y.shape[1]
-    img = y.view(n, h, w, c).permute(0, 3, 1, 2)                       # NCHW shape, channels_last strides: no copy
-    t = F.conv2d(img, blk.dwconv.weight.float(), blk.dwconv.bias.float(), padding=blk.dwconv.padding, groups=c)
-    t = ln_rows(_rows(t), blk.norm.weight, blk.norm.bias, blk.norm.eps, None, out_bf16=True)
+    if blk.dwconv.kernel_size == (7, 7) and dwconv7_ok(c, h, w):
+        t = dwconv7_rows(y, blk.dwconv.weight, blk.dwconv.bias, n, h, w)               # csrc/dwconv.cu, rows in, rows out
+    else:
+        img = y.view(n, h, w, c).permute(0, 3, 1, 2)                   # NCHW shape, channels_last strides: no copy
+        t = _rows(F.conv2d(img, blk.dwconv.weight.float(), blk.dwconv.bias.float(), padding=blk.dwconv.padding, groups=c))
+    t = ln_rows(t, blk.norm.weight, blk.norm.bias, blk.norm.eps, None, out_bf16=True)
     hdn = linear(t, blk.pwconv1.weight, blk.pwconv1.bias, "gelu")
     # gamma * pwconv2(.) + input: layer scale and skip connection in the GEMM epilogue
     return linear(hdn, blk.pwconv2.weight, blk.pwconv2.bias, None, None, None, blk.gamma, y)

@@ -303,6 +303,17 @@ int cor_ln_rows_fwd(const float* x, const float* weight, const float* bias, long
 int cor_ln_rows_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* stats,
                     long long rows, int C, int act, float* dx, float* dweight, float* dbias, void* work, cor_stream_t stream);
 
+/* Depth-wise 7x7 convolution (padding 3, stride 1) on channels-last maps [n][h][w][C] f32 (csrc/dwconv.cu): the spatial
+ * step of the ConvNeXt blocks (lib/support_model/mask_adapter.py:196-199).  weight [C][49] (nn.Conv2d's [C,1,7,7]), bias [C] or
+ * NULL; flip = 1 applies the kernel rotated by 180 degrees = the gradient w.r.t. the input when `in` is d out.
+ * cor_dwconv7_cl_wgrad: dweight [C][49] and dbias [C] (may be NULL) from (in, d out); work: cor_dwconv7_work_bytes().
+ * C % 32 == 0; the row band + halo of 32 channels must fit shared memory (w <= ~300). */
+size_t cor_dwconv7_work_bytes(int n, int h, int w, int C);
+int cor_dwconv7_cl(const float* in, const float* weight, const float* bias, float* out, int n, int h, int w, int C, int flip,
+                   cor_stream_t stream);
+int cor_dwconv7_cl_wgrad(const float* in, const float* dout, float* dweight, float* dbias, int n, int h, int w, int C, void* work,
+                         cor_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Mask-logit producer: the hypernetwork product of the SAM decoder,
  *   masks[b, t, p] = sum_c hyper_in[b, t0 + t, c] * upscaled[b, c, p]     lib/sam_model/mask_decoder.py:135-137

@@ -80,3 +80,49 @@ def test_adapter_backward_vs_reference_module():
     total = rel(flat([p for _, p in ours.named_parameters()]), flat([pr[n] for n, _ in ours.named_parameters()]))
     assert total < 3e-2, (total, sorted(worst.items(), key=lambda kv: -kv[1])[:5])
     assert max(worst.values()) < 2e-1, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
+@pytest.mark.parametrize("shape", [(3, 24, 24, 256), (2, 9, 30, 64), (1, 40, 17, 32)])
+def test_depthwise_7x7_channels_last_vs_torch(shape):
+    """cor_dwconv7_cl forward / input gradient / weight gradient against F.conv2d(groups=C) in fp32."""
+    import torch.nn.functional as F
+    from cor_b200.linear import dwconv7_rows
+    n, h, w, C = shape
+    g = torch.Generator(device=dev()).manual_seed(h * w)
+    x = torch.randn(n * h * w, C, device=dev(), generator=g, requires_grad=True)
+    wt = (0.2 * torch.randn(C, 1, 7, 7, device=dev(), generator=g)).requires_grad_(True)
+    b = torch.randn(C, device=dev(), generator=g, requires_grad=True)
+    y = dwconv7_rows(x, wt, b, n, h, w)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    x2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, wt, b))
+    ref = F.conv2d(x2.view(n, h, w, C).permute(0, 3, 1, 2), w2, b2, padding=3, groups=C).permute(0, 2, 3, 1).reshape(n * h * w, C)
+    ref.backward(gy)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(x.grad, x2.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(wt.grad, w2.grad, rtol=2e-4, atol=2e-3)
+    torch.testing.assert_close(b.grad, b2.grad, rtol=2e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("shape", [(1000, 512), (77, 256), (33, 1000)])
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_ln_rows_forward_backward_vs_torch(shape, act):
+    import torch.nn.functional as F
+    from cor_b200.linear import ln_rows
+    rows, C = shape
+    g = torch.Generator(device=dev()).manual_seed(rows)
+    x = (2 * torch.randn(rows, C, device=dev(), generator=g) + 0.5).requires_grad_(True)
+    wt = (1 + 0.2 * torch.randn(C, device=dev(), generator=g)).requires_grad_(True)
+    b = (0.3 * torch.randn(C, device=dev(), generator=g)).requires_grad_(True)
+    y = ln_rows(x, wt, b, 1e-6, act)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    x2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, wt, b))
+    ref = F.layer_norm(x2, (C,), w2, b2, 1e-6)
+    if act == "gelu":
+        ref = F.gelu(ref)
+    ref.backward(gy)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(x.grad, x2.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(wt.grad, w2.grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(b.grad, b2.grad, rtol=1e-3, atol=1e-3)
