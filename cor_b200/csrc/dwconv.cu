@@ -98,8 +98,20 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_wgrad_kernel(const float
     float acc = 0.f;
     if (k < kDwT) {
       const int dy = k / kDwK, dx = k % kDwK;
-      for (int y = 0; y < rows; ++y)
-        for (int x = 0; x < w; ++x) acc = fmaf(gt[(y * w + x) * kDwCG + lane], xt[((y + dy) * tw + x + dx) * kDwCG + lane], acc);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains: the loop is FMA-latency bound otherwise
+      for (int y = 0; y < rows; ++y) {
+        const float* gr = gt + (size_t)y * w * kDwCG + lane;
+        const float* xr = xt + ((size_t)(y + dy) * tw + dx) * kDwCG + lane;
+        int x = 0;
+        for (; x + 4 <= w; x += 4) {
+          a0 = fmaf(gr[(x + 0) * kDwCG], xr[(x + 0) * kDwCG], a0);
+          a1 = fmaf(gr[(x + 1) * kDwCG], xr[(x + 1) * kDwCG], a1);
+          a2 = fmaf(gr[(x + 2) * kDwCG], xr[(x + 2) * kDwCG], a2);
+          a3 = fmaf(gr[(x + 3) * kDwCG], xr[(x + 3) * kDwCG], a3);
+        }
+        for (; x < w; ++x) a0 = fmaf(gr[x * kDwCG], xr[x * kDwCG], a0);
+      }
+      acc = (a0 + a1) + (a2 + a3);
     } else {
       for (int i = 0; i < rows * w; ++i) acc += gt[i * kDwCG + lane];
     }

@@ -202,6 +202,69 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
           return;
         }
         float o[32];
+        const bool fast = nb + 32 <= g.N && g.N % 8 == 0 && g.ldc % 8 == 0 && (!g.residual || g.ldr % 8 == 0);
+        if (fast) {
+          // whole 32-column chunk, 16-byte aligned rows: every per-column / per-element operand moves as 128-bit vectors
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * g.alpha;
+          if (g.bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(g.bias + nb) + j);
+              o[4 * j] += t.x; o[4 * j + 1] += t.y; o[4 * j + 2] += t.z; o[4 * j + 3] += t.w;
+            }
+          }
+          if (g.pre) {
+            uint4* dstp = reinterpret_cast<uint4*>(g.pre + row * g.ldc + nb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 pk = __floats2bfloat162_rn(o[8 * j + 2 * q], o[8 * j + 2 * q + 1]);
+                w[q] = *reinterpret_cast<uint32_t*>(&pk);
+              }
+              dstp[j] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          if (g.act != COR_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = gemm_act(o[j], g.act);
+          }
+          if (g.emul) {
+            const float4* e = reinterpret_cast<const float4*>(g.emul + row * g.N + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = e[j];
+              o[4 * j] *= t.x; o[4 * j + 1] *= t.y; o[4 * j + 2] *= t.z; o[4 * j + 3] *= t.w;
+            }
+          }
+          if (g.colscale) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(g.colscale + nb) + j);
+              o[4 * j] *= t.x; o[4 * j + 1] *= t.y; o[4 * j + 2] *= t.z; o[4 * j + 3] *= t.w;
+            }
+          }
+          if (g.residual) {
+            if (g.res_bf16) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + row * g.ldr + nb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 t = r4[j];
+                o[8 * j] += bf16lo(t.x); o[8 * j + 1] += bf16hi(t.x); o[8 * j + 2] += bf16lo(t.y); o[8 * j + 3] += bf16hi(t.y);
+                o[8 * j + 4] += bf16lo(t.z); o[8 * j + 5] += bf16hi(t.z); o[8 * j + 6] += bf16lo(t.w); o[8 * j + 7] += bf16hi(t.w);
+              }
+            } else {
+              const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + row * g.ldr + nb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = r4[j];
+                o[4 * j] += t.x; o[4 * j + 1] += t.y; o[4 * j + 2] += t.z; o[4 * j + 3] += t.w;
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = nb + j;
@@ -217,6 +280,7 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
                               : reinterpret_cast<const float*>(g.residual)[row * g.ldr + n];
           }
           o[j] = x;
+        }
         }
         const bool full = nb + 32 <= g.N;
         if (g.c_bf16) {

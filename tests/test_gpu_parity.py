@@ -59,8 +59,10 @@ def test_mask_adapter_tail_golden():
 
 
 def test_mask_adapter_module_matches_oracle_with_shared_weights():
-    """Whole MaskAdapterPooling module (head on cuDNN, tail on our kernel) vs the ATen port of the tail."""
-    from cor_b200.mask_adapter import MaskAdapterPooling
+    """Whole MaskAdapterPooling module vs the ATen port of the tail: exactly, on the maps our learned half produces
+    (cor_b200.mask_adapter.adapter_maps: bf16-operand GEMMs), and within the bf16 operand rounding on the maps of the module's
+    eager fp32 definition.  tests/test_gpu_adapter.py checks the learned half against the reference module itself."""
+    from cor_b200.mask_adapter import MaskAdapterPooling, adapter_maps
     from oracle import aten_port as ap
     torch.manual_seed(0)
     mod = MaskAdapterPooling(x_in_channel=48, mask_adatpet_network_in_channel=32, mask_downscaling_mid_channel=16,
@@ -72,8 +74,9 @@ def test_mask_adapter_module_matches_oracle_with_shared_weights():
     with torch.no_grad():
         m = torch.nn.functional.interpolate(mask, size=(24, 24), mode="bilinear", align_corners=False)
         maps = mod.get_mask_map(mod.channel_clip_to_maskadapter(feat), m)
-    ref = ap.softmax_map_pool(maps.cpu(), feat.cpu(), 8)
-    close(out, ref.numpy(), rtol=1e-4, atol=1e-5)
+        maps_ours = adapter_maps(mod, feat, m)
+    close(out, ap.softmax_map_pool(maps_ours.cpu(), feat.cpu(), 8).numpy(), rtol=1e-4, atol=1e-5)
+    close(out, ap.softmax_map_pool(maps.cpu(), feat.cpu(), 8).numpy(), rtol=2e-2, atol=2e-3)
     out.sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mod.parameters())
 

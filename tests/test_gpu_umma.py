@@ -303,3 +303,26 @@ def test_tensor_core_paths_from_a_thread_without_a_cuda_context():
     r2, q2 = cu(g2["regions"], grad=True), cu(g2["queries"], grad=True)
     ops.infonce_loss(r2, q2, cu((np.arange(256) * 3) % 4096), tau=0.07).backward()
     assert torch.isfinite(r2.grad).all() and torch.isfinite(q2.grad).all()
+
+
+def test_captured_step_with_tensor_core_similarity_replays_bit_equal():
+    """At 8 GPUs the gathered gallery (>= 8192 rows) sends the fused step's similarity stage to the tcgen05 kernel with the
+    queries in tensor memory (sim_umma_ts.cu); here the same path is forced on one GPU (sim_engine="umma") and captured
+    into a CUDA graph: replays must reproduce the eager step bit for bit, loss and all three gradients."""
+    from cor_b200 import region, synth
+    d = synth.make_triplets(91, B=4, M=32, C=256, h=16, w=16, H=64, W=64, hp=32, wp=32, degenerate=False)
+    t = {k: torch.from_numpy(v).to(dev()) for k, v in d.items()}
+    t["emb"] = t["emb"].bfloat16()
+    bufs = region.StepBuffers(4, 32, C=256, h=16, w=16, H=64, W=64, hp=32, wp=32, device=dev(), emb_dtype=torch.bfloat16)
+    bufs.load(t)
+    kw = dict(gather=False, sim_engine="umma")
+    loss_e, grads_e = bufs._step(True, True, kw)
+    loss_e = loss_e.clone()
+    grads_e = {k: v.clone() for k, v in grads_e.items()}
+    bufs.capture(**kw)
+    for _ in range(3):
+        bufs.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(bufs.loss.reshape(()), loss_e.reshape(()))
+    for k in ("pred", "emb", "comb"):
+        assert torch.equal(bufs.grads[k], grads_e[k]), k
