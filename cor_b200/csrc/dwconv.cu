@@ -26,6 +26,29 @@ __host__ __device__ inline int dw_band_rows(int h, int w, int tiles) {
   return r < 1 ? 1 : r;
 }
 
+// Stage rows [y0 - pad, y0 + rows + pad) x [-pad, w + pad) of one image's 32-channel slice into shared memory
+// ([pixel][32]), zeros outside the image.  Four pixels (4 x 128 B) in flight per warp: the staging is pure load latency.
+__device__ __forceinline__ void stage_tile(float* __restrict__ tile, const float* __restrict__ src, int C, int c, int h, int w, int y0,
+                                           int rows, int pad, int warp, int lane) {
+  const int tw = w + 2 * pad, total = (rows + 2 * pad) * tw;
+  constexpr int U = 4, NW = kDwThreads / 32;
+  for (int i0 = warp; i0 < total; i0 += U * NW) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * NW;
+      const int ty = i / tw, tx = i - ty * tw;
+      const int gy = y0 + ty - pad, gx = tx - pad;
+      v[u] = (i < total && gy >= 0 && gy < h && gx >= 0 && gx < w) ? src[((long long)gy * w + gx) * C + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * NW;
+      if (i < total) tile[i * kDwCG + lane] = v[u];
+    }
+  }
+}
+
 // grid = (bands, C / 32, n)
 template <bool FLIP>
 __global__ void __launch_bounds__(kDwThreads) dwconv_cl_kernel(const float* __restrict__ in, const float* __restrict__ wt,
@@ -38,11 +61,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_kernel(const float* __re
   const int y0 = blockIdx.x * band, rows = min(band, h - y0);
   const int tw = w + 2 * kDwR, th = rows + 2 * kDwR;
   const float* src = in + (long long)n * h * w * C;
-  for (int i = warp; i < th * tw; i += kDwThreads / 32) {
-    const int ty = i / tw, tx = i % tw;
-    const int gy = y0 + ty - kDwR, gx = tx - kDwR;
-    tile[i * kDwCG + lane] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? src[((long long)gy * w + gx) * C + c] : 0.f;
-  }
+  (void)th;
+  stage_tile(tile, src, C, c, h, w, y0, rows, kDwR, warp, lane);
   float wreg[kDwT];
 #pragma unroll
   for (int k = 0; k < kDwT; ++k) wreg[k] = wt[(long long)c * kDwT + (FLIP ? kDwT - 1 - k : k)];
@@ -73,6 +93,10 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_kernel(const float* __re
 }
 
 // grid = (bands, C / 32, n): partial[(n * bands + band)][C][50] = {d w[49], d bias}
+// Warp w takes output rows y = w, w + 8, ...; lane = channel keeps all 49 tap sums (+ the bias sum) in registers.  For a
+// chunk of 8 adjacent outputs the 8 gradients and, per kernel row, 14 inputs are loaded once and feed 7 x 8 FMAs each
+// (3.7 FMAs per shared load; one tap per warp with two loads per FMA made the kernel shared-memory bound).  The 8 warps'
+// sums are folded in fixed order through shared memory.
 __global__ void __launch_bounds__(kDwThreads) dwconv_cl_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dout,
                                                                      float* __restrict__ part, int h, int w, int C, int band) {
   extern __shared__ float sm[];                         // X tile [(rows + 6)][(w + 6)][32] then dY tile [rows][w][32]
@@ -80,42 +104,46 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_wgrad_kernel(const float
   const int c = blockIdx.y * kDwCG + lane;
   const int n = blockIdx.z;
   const int y0 = blockIdx.x * band, rows = min(band, h - y0);
-  const int tw = w + 2 * kDwR, th = rows + 2 * kDwR;
+  const int tw = w + 2 * kDwR;
   float* xt = sm;
   float* gt = sm + (size_t)(band + 2 * kDwR) * tw * kDwCG;
-  const float* src = in + (long long)n * h * w * C;
-  const float* gsrc = dout + (long long)n * h * w * C;
-  for (int i = warp; i < th * tw; i += kDwThreads / 32) {
-    const int ty = i / tw, tx = i % tw;
-    const int gy = y0 + ty - kDwR, gx = tx - kDwR;
-    xt[i * kDwCG + lane] = (gy >= 0 && gy < h && gx >= 0 && gx < w) ? src[((long long)gy * w + gx) * C + c] : 0.f;
+  stage_tile(xt, in + (long long)n * h * w * C, C, c, h, w, y0, rows, kDwR, warp, lane);
+  stage_tile(gt, dout + (long long)n * h * w * C, C, c, h, w, y0, rows, 0, warp, lane);
+  __syncthreads();
+  float acc[kDwT + 1];
+#pragma unroll
+  for (int k = 0; k <= kDwT; ++k) acc[k] = 0.f;
+  for (int y = warp; y < rows; y += kDwThreads / 32) {
+    for (int x0 = 0; x0 < w; x0 += 8) {
+      float g[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g[j] = (x0 + j < w) ? gt[((size_t)y * w + x0 + j) * kDwCG + lane] : 0.f;
+        acc[kDwT] += g[j];
+      }
+#pragma unroll
+      for (int dy = 0; dy < kDwK; ++dy) {
+        const float* xr = xt + ((size_t)(y + dy) * tw + x0) * kDwCG + lane;
+        float v[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) v[j] = (x0 + j < tw) ? xr[j * kDwCG] : 0.f;
+#pragma unroll
+        for (int dx = 0; dx < kDwK; ++dx)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[dy * kDwK + dx] = fmaf(g[j], v[j + dx], acc[dy * kDwK + dx]);
+      }
+    }
   }
-  for (int i = warp; i < rows * w; i += kDwThreads / 32) gt[i * kDwCG + lane] = gsrc[((long long)(y0 + i / w) * w + i % w) * C + c];
+  __syncthreads();                                       // tiles consumed: their memory becomes the fold scratch
+  float* red = sm;                                       // [8 warps][50][32]
+#pragma unroll
+  for (int k = 0; k <= kDwT; ++k) red[(warp * (kDwT + 1) + k) * kDwCG + lane] = acc[k];
   __syncthreads();
   float* o = part + (((long long)n * gridDim.x + blockIdx.x) * C + c) * (kDwT + 1);
-  // warp w takes taps w, w + 8, ...; tap 49 is the bias (sum of d out)
   for (int k = warp; k <= kDwT; k += kDwThreads / 32) {
-    float acc = 0.f;
-    if (k < kDwT) {
-      const int dy = k / kDwK, dx = k % kDwK;
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains: the loop is FMA-latency bound otherwise
-      for (int y = 0; y < rows; ++y) {
-        const float* gr = gt + (size_t)y * w * kDwCG + lane;
-        const float* xr = xt + ((size_t)(y + dy) * tw + dx) * kDwCG + lane;
-        int x = 0;
-        for (; x + 4 <= w; x += 4) {
-          a0 = fmaf(gr[(x + 0) * kDwCG], xr[(x + 0) * kDwCG], a0);
-          a1 = fmaf(gr[(x + 1) * kDwCG], xr[(x + 1) * kDwCG], a1);
-          a2 = fmaf(gr[(x + 2) * kDwCG], xr[(x + 2) * kDwCG], a2);
-          a3 = fmaf(gr[(x + 3) * kDwCG], xr[(x + 3) * kDwCG], a3);
-        }
-        for (; x < w; ++x) a0 = fmaf(gr[x * kDwCG], xr[x * kDwCG], a0);
-      }
-      acc = (a0 + a1) + (a2 + a3);
-    } else {
-      for (int i = 0; i < rows * w; ++i) acc += gt[i * kDwCG + lane];
-    }
-    o[k] = acc;
+    float sacc = 0.f;
+    for (int wv = 0; wv < kDwThreads / 32; ++wv) sacc += red[(wv * (kDwT + 1) + k) * kDwCG + lane];
+    o[k] = sacc;
   }
 }
 

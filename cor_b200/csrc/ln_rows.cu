@@ -19,7 +19,7 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-template <typename TO>
+template <typename TO, int PL>      // PL = values per lane: C <= 32 * PL
 __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                     const float* __restrict__ b, long long rows, int C, float eps, int act,
                                                                     TO* __restrict__ y, float* __restrict__ stats) {
@@ -27,10 +27,10 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_fwd_kernel(const float*
   const long long row = (long long)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = x + row * C;
-  float v[kLnMaxPerLane];
+  float v[PL];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PL; ++i) {
     const int c = lane + 32 * i;
     v[i] = c < C ? xr[c] : 0.f;
     s += v[i];
@@ -38,14 +38,14 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_fwd_kernel(const float*
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PL; ++i) {
     const int c = lane + 32 * i;
     const float d = c < C ? v[i] - mean : 0.f;
     q = fmaf(d, d, q);
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PL; ++i) {
     const int c = lane + 32 * i;
     if (c < C) {
       float o = (v[i] - mean) * rstd * w[c] + b[c];
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_fwd_kernel(const float*
 }
 
 // dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * act'(.) * w;  dw_part / db_part [gridDim.x][C]
+template <int PL>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ w, const float* __restrict__ b,
                                                                     const float* __restrict__ stats, long long rows, int C, int act,
@@ -65,16 +66,16 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const float*
   __shared__ float red[kLnWarps][2];
   extern __shared__ float acc_s[];             // [2][kLnWarps][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float aw[kLnMaxPerLane], ab[kLnMaxPerLane];
+  float aw[PL], ab[PL];
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) aw[i] = ab[i] = 0.f;
+  for (int i = 0; i < PL; ++i) aw[i] = ab[i] = 0.f;
   const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   for (long long row = r0 + warp; row < r1; row += kLnWarps) {
     const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-    float g[kLnMaxPerLane], xh[kLnMaxPerLane];
+    float g[PL], xh[PL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < PL; ++i) {
       const int c = lane + 32 * i;
       g[i] = xh[i] = 0.f;
       if (c < C) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const float*
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
+    for (int i = 0; i < PL; ++i) {
       const int c = lane + 32 * i;
       if (c < C) dx[row * C + c] = rstd * (g[i] - s1 - xh[i] * s2);
     }
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const float*
   (void)red;
   // fold the 8 warps' column sums in fixed order, publish this CTA's partial
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i) {
+  for (int i = 0; i < PL; ++i) {
     const int c = lane + 32 * i;
     if (c < C) { acc_s[warp * C + c] = aw[i]; acc_s[(kLnWarps + warp) * C + c] = ab[i]; }
   }
@@ -142,9 +143,11 @@ extern "C" int cor_ln_rows_fwd(const float* x, const float* weight, const float*
   COR_REQUIRE(act == COR_ACT_NONE || act == COR_ACT_GELU, "cor_ln_rows_fwd: act %d", act);
   const unsigned blocks = (unsigned)((rows + kLnWarps - 1) / kLnWarps);
   cudaStream_t st = as_stream(stream);
-  if (y_dtype == COR_F32) ln_rows_fwd_kernel<float><<<blocks, kLnWarps * 32, 0, st>>>(x, weight, bias, rows, C, eps, act, (float*)y, stats);
-  else if (y_dtype == COR_BF16) ln_rows_fwd_kernel<bf16><<<blocks, kLnWarps * 32, 0, st>>>(x, weight, bias, rows, C, eps, act, (bf16*)y, stats);
-  else COR_REQUIRE(false, "cor_ln_rows_fwd: output dtype %d", y_dtype);
+  COR_REQUIRE(y_dtype == COR_F32 || y_dtype == COR_BF16, "cor_ln_rows_fwd: output dtype %d", y_dtype);
+#define COR_LN_F(TO, PL) ln_rows_fwd_kernel<TO, PL><<<blocks, kLnWarps * 32, 0, st>>>(x, weight, bias, rows, C, eps, act, (TO*)y, stats)
+  if (y_dtype == COR_F32) { if (C <= 256) COR_LN_F(float, 8); else if (C <= 512) COR_LN_F(float, 16); else COR_LN_F(float, 32); }
+  else { if (C <= 256) COR_LN_F(bf16, 8); else if (C <= 512) COR_LN_F(bf16, 16); else COR_LN_F(bf16, 32); }
+#undef COR_LN_F
   return check_launch("ln_rows_fwd_kernel");
 }
 
@@ -158,8 +161,13 @@ extern "C" int cor_ln_rows_bwd(const float* dy, const float* x, const float* wei
   float* dbp = dwp + (size_t)parts * C;
   cudaStream_t st = as_stream(stream);
   const size_t smem = (size_t)2 * kLnWarps * C * sizeof(float);
-  COR_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ln_rows_bwd_kernel<<<parts, kLnWarps * 32, smem, st>>>(dy, x, weight, bias, stats, rows, C, act, per, dx, dwp, dbp);
+#define COR_LN_B(PL)                                                                                                              \
+  do {                                                                                                                            \
+    COR_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    ln_rows_bwd_kernel<PL><<<parts, kLnWarps * 32, smem, st>>>(dy, x, weight, bias, stats, rows, C, act, per, dx, dwp, dbp);      \
+  } while (0)
+  if (C <= 256) COR_LN_B(8); else if (C <= 512) COR_LN_B(16); else COR_LN_B(32);
+#undef COR_LN_B
   int rc = check_launch("ln_rows_bwd_kernel");
   if (rc) return rc;
   ln_fold_kernel<<<(C + 127) / 128, 128, 0, st>>>(dwp, dbp, parts, C, dweight, dbias);
