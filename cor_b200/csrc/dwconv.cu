@@ -16,35 +16,41 @@ namespace cor {
 constexpr int kDwK = 7, kDwR = 3, kDwT = kDwK * kDwK;
 constexpr int kDwCG = 32;                 // channels per CTA
 constexpr int kDwThreads = 256;
-constexpr int kDwSmemBudget = 160 * 1024;
+constexpr int kDwFwdBudget = 56 * 1024;    // shared memory per CTA: four forward CTAs / two weight-gradient CTAs per SM, so that
+constexpr int kDwWgBudget = 104 * 1024;    // one CTA's staging (pure load latency) runs under another's arithmetic
 
-__host__ __device__ inline int dw_band_rows(int h, int w, int tiles) {
-  // rows per band so that `tiles` padded tiles ((rows + 6) x (w + 6) x 32 floats each) fit the budget
-  const int per_row = (w + 2 * kDwR) * kDwCG * 4 * tiles;
-  int r = kDwSmemBudget / per_row - 2 * kDwR;
+__host__ __device__ inline int dw_band_rows(int h, int w, int wgrad) {
+  // rows per band: forward needs (rows + 6) x (w + 6) x 32 floats, the weight gradient additionally rows x w x 32
+  int r;
+  if (wgrad) r = (kDwWgBudget / (kDwCG * 4) - 2 * kDwR * (w + 2 * kDwR)) / (2 * w + 2 * kDwR);
+  else r = kDwFwdBudget / ((w + 2 * kDwR) * kDwCG * 4) - 2 * kDwR;
   if (r > h) r = h;
   return r < 1 ? 1 : r;
 }
 
 // Stage rows [y0 - pad, y0 + rows + pad) x [-pad, w + pad) of one image's 32-channel slice into shared memory
-// ([pixel][32]), zeros outside the image.  Four pixels (4 x 128 B) in flight per warp: the staging is pure load latency.
-__device__ __forceinline__ void stage_tile(float* __restrict__ tile, const float* __restrict__ src, int C, int c, int h, int w, int y0,
-                                           int rows, int pad, int warp, int lane) {
+// ([pixel][32]), zeros outside the image.  All 256 threads take part: 8 threads move one pixel's 128 bytes as float4s,
+// 32 pixels per pass, 4 passes in flight (16 KB per CTA): the staging is pure load latency.
+__device__ __forceinline__ void stage_tile(float* __restrict__ tile, const float* __restrict__ src, int C, int c0, int h, int w, int y0,
+                                           int rows, int pad) {
   const int tw = w + 2 * pad, total = (rows + 2 * pad) * tw;
-  constexpr int U = 4, NW = kDwThreads / 32;
-  for (int i0 = warp; i0 < total; i0 += U * NW) {
-    float v[U];
+  const int sub = threadIdx.x >> 3, ch4 = (threadIdx.x & 7) * 4;
+  constexpr int U = 4, PP = kDwThreads / 8;
+  for (int i0 = sub; i0 < total; i0 += U * PP) {
+    float4 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * NW;
+      const int i = i0 + u * PP;
       const int ty = i / tw, tx = i - ty * tw;
       const int gy = y0 + ty - pad, gx = tx - pad;
-      v[u] = (i < total && gy >= 0 && gy < h && gx >= 0 && gx < w) ? src[((long long)gy * w + gx) * C + c] : 0.f;
+      v[u] = (i < total && gy >= 0 && gy < h && gx >= 0 && gx < w)
+                 ? __ldg(reinterpret_cast<const float4*>(src + ((long long)gy * w + gx) * C + c0 + ch4))
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * NW;
-      if (i < total) tile[i * kDwCG + lane] = v[u];
+      const int i = i0 + u * PP;
+      if (i < total) *reinterpret_cast<float4*>(tile + (size_t)i * kDwCG + ch4) = v[u];
     }
   }
 }
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_kernel(const float* __re
   const int tw = w + 2 * kDwR, th = rows + 2 * kDwR;
   const float* src = in + (long long)n * h * w * C;
   (void)th;
-  stage_tile(tile, src, C, c, h, w, y0, rows, kDwR, warp, lane);
+  stage_tile(tile, src, C, blockIdx.y * kDwCG, h, w, y0, rows, kDwR);
   float wreg[kDwT];
 #pragma unroll
   for (int k = 0; k < kDwT; ++k) wreg[k] = wt[(long long)c * kDwT + (FLIP ? kDwT - 1 - k : k)];
@@ -107,8 +113,8 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_wgrad_kernel(const float
   const int tw = w + 2 * kDwR;
   float* xt = sm;
   float* gt = sm + (size_t)(band + 2 * kDwR) * tw * kDwCG;
-  stage_tile(xt, in + (long long)n * h * w * C, C, c, h, w, y0, rows, kDwR, warp, lane);
-  stage_tile(gt, dout + (long long)n * h * w * C, C, c, h, w, y0, rows, 0, warp, lane);
+  stage_tile(xt, in + (long long)n * h * w * C, C, blockIdx.y * kDwCG, h, w, y0, rows, kDwR);
+  stage_tile(gt, dout + (long long)n * h * w * C, C, blockIdx.y * kDwCG, h, w, y0, rows, 0);
   __syncthreads();
   float acc[kDwT + 1];
 #pragma unroll
@@ -163,7 +169,7 @@ __global__ void dwconv_fold_kernel(const float* __restrict__ part, int nparts, i
 using namespace cor;
 
 extern "C" size_t cor_dwconv7_work_bytes(int n, int h, int w, int C) {
-  const int bands = ceil_div(h, dw_band_rows(h, w, 2));
+  const int bands = ceil_div(h, dw_band_rows(h, w, 1));
   return (size_t)n * bands * C * (kDwT + 1) * sizeof(float) + 16;
 }
 
@@ -171,7 +177,7 @@ extern "C" int cor_dwconv7_cl(const float* in, const float* weight, const float*
                               cor_stream_t stream) {
   COR_REQUIRE(in && weight && out, "cor_dwconv7_cl: null pointer");
   COR_REQUIRE(n > 0 && h > 0 && w > 0 && C > 0 && C % kDwCG == 0, "cor_dwconv7_cl: need C %% 32 == 0 (C=%d)", C);
-  const int band = dw_band_rows(h, w, 1);
+  const int band = dw_band_rows(h, w, 0);
   const size_t smem = (size_t)(band + 2 * kDwR) * (w + 2 * kDwR) * kDwCG * sizeof(float);
   COR_REQUIRE(smem <= 200 * 1024, "cor_dwconv7_cl: map too wide (w=%d)", w);
   const dim3 grid(ceil_div(h, band), C / kDwCG, n);
@@ -190,7 +196,7 @@ extern "C" int cor_dwconv7_cl_wgrad(const float* in, const float* dout, float* d
                                     cor_stream_t stream) {
   COR_REQUIRE(in && dout && dweight && work, "cor_dwconv7_cl_wgrad: null pointer");
   COR_REQUIRE(n > 0 && h > 0 && w > 0 && C > 0 && C % kDwCG == 0, "cor_dwconv7_cl_wgrad: need C %% 32 == 0 (C=%d)", C);
-  const int band = dw_band_rows(h, w, 2);
+  const int band = dw_band_rows(h, w, 1);
   const size_t smem = ((size_t)(band + 2 * kDwR) * (w + 2 * kDwR) + (size_t)band * w) * kDwCG * sizeof(float);
   COR_REQUIRE(smem <= 220 * 1024, "cor_dwconv7_cl_wgrad: map too wide (w=%d)", w);
   const int bands = ceil_div(h, band);
