@@ -98,13 +98,13 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_gemm_bf16", i, p, i, ll, ll, p, i, ll, ll, i, i, i, i, f, p, i, p, p, p, i, ll, p, i, ll, p, i, p, p)
         _sig(lib, "cor_cast_cat_bf16", i, p, i, p, i, ll, p, p)
         _sig(lib, "cor_act_bwd_work_bytes", sz, ll, i)
-        _sig(lib, "cor_act_bwd", i, p, p, p, p, p, i, ll, i, p, p, p, p, p)
+        _sig(lib, "cor_act_bwd", i, p, i, p, p, p, p, i, ll, i, p, p, p, p, p)
         _sig(lib, "cor_dwconv7_work_bytes", sz, i, i, i, i)
         _sig(lib, "cor_dwconv7_cl", i, p, p, p, p, i, i, i, i, i, p)
         _sig(lib, "cor_dwconv7_cl_wgrad", i, p, p, p, p, i, i, i, i, p, p)
         _sig(lib, "cor_ln_rows_work_bytes", sz, ll, i)
         _sig(lib, "cor_ln_rows_fwd", i, p, p, p, ll, i, f, i, p, i, p, p)
-        _sig(lib, "cor_ln_rows_bwd", i, p, p, p, p, p, ll, i, i, p, p, p, p, p)
+        _sig(lib, "cor_ln_rows_bwd", i, p, i, p, p, p, p, ll, i, i, p, p, p, p, p)
         _sig(lib, "cor_hyper_logits_work_bytes", sz, i, i, i, ll)
         _sig(lib, "cor_hyper_logits_fwd", i, p, p, i, p, i, i, i, i, i, i, ll, p)
         _sig(lib, "cor_hyper_logits_bwd", i, p, p, i, p, i, p, p, i, i, i, i, i, ll, p, p)

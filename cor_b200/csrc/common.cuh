@@ -83,6 +83,33 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
+// Sum over `nparts` partial rows of column c (part[k * ld + c]) by a (32, kFoldTy) thread block: thread row ty takes
+// k = ty, ty + kFoldTy, ... with four independent accumulators (loads pipeline; a single serial chain over ~2000 partials
+// cost 100 us), then the kFoldTy row sums are added in fixed order.  Deterministic; the total is returned to ty == 0.
+constexpr int kFoldTy = 16;
+__device__ __forceinline__ float fold_parts(const float* __restrict__ part, int nparts, long long ld, long long c, bool ok,
+                                            float (*sm)[32]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (ok) {
+    int k = threadIdx.y;
+    for (; k + 3 * kFoldTy < nparts; k += 4 * kFoldTy) {
+      s0 += part[(long long)k * ld + c];
+      s1 += part[(long long)(k + kFoldTy) * ld + c];
+      s2 += part[(long long)(k + 2 * kFoldTy) * ld + c];
+      s3 += part[(long long)(k + 3 * kFoldTy) * ld + c];
+    }
+    for (; k < nparts; k += kFoldTy) s0 += part[(long long)k * ld + c];
+  }
+  sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int j = 0; j < kFoldTy; ++j) t += sm[j][threadIdx.x];
+  }
+  return t;
+}
+
 // Block-wide sum of NV values per thread; result valid in every thread.  `scratch` needs
 // NV * 32 floats.  Deterministic (fixed tree).
 template <int NV, typename T>

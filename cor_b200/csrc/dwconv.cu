@@ -19,11 +19,15 @@ constexpr int kDwThreads = 256;
 constexpr int kDwFwdBudget = 56 * 1024;    // shared memory per CTA: four forward CTAs / two weight-gradient CTAs per SM, so that
 constexpr int kDwWgBudget = 104 * 1024;    // one CTA's staging (pure load latency) runs under another's arithmetic
 
+// Tile rows are padded on the right to a whole number of output groups (4 outputs forward, 8 in the weight gradient) so
+// the inner loops load without bounds predicates; the padding holds zeros.
+__host__ __device__ inline int dw_pad(int w, int blk) { return (w + blk - 1) / blk * blk; }
 __host__ __device__ inline int dw_band_rows(int h, int w, int wgrad) {
-  // rows per band: forward needs (rows + 6) x (w + 6) x 32 floats, the weight gradient additionally rows x w x 32
+  // rows per band: forward needs (rows + 6) x (pad4(w) + 6) x 32 floats, the weight gradient (rows + 6) x (pad8(w) + 6)
+  // + rows x pad8(w)
   int r;
-  if (wgrad) r = (kDwWgBudget / (kDwCG * 4) - 2 * kDwR * (w + 2 * kDwR)) / (2 * w + 2 * kDwR);
-  else r = kDwFwdBudget / ((w + 2 * kDwR) * kDwCG * 4) - 2 * kDwR;
+  if (wgrad) r = (kDwWgBudget / (kDwCG * 4) - 2 * kDwR * (dw_pad(w, 8) + 2 * kDwR)) / (2 * dw_pad(w, 8) + 2 * kDwR);
+  else r = kDwFwdBudget / ((dw_pad(w, 4) + 2 * kDwR) * kDwCG * 4) - 2 * kDwR;
   if (r > h) r = h;
   return r < 1 ? 1 : r;
 }
@@ -32,8 +36,8 @@ __host__ __device__ inline int dw_band_rows(int h, int w, int wgrad) {
 // ([pixel][32]), zeros outside the image.  All 256 threads take part: 8 threads move one pixel's 128 bytes as float4s,
 // 32 pixels per pass, 4 passes in flight (16 KB per CTA): the staging is pure load latency.
 __device__ __forceinline__ void stage_tile(float* __restrict__ tile, const float* __restrict__ src, int C, int c0, int h, int w, int y0,
-                                           int rows, int pad) {
-  const int tw = w + 2 * pad, total = (rows + 2 * pad) * tw;
+                                           int rows, int pad, int tw) {      // tw = tile row stride in pixels, >= w + 2 pad
+  const int total = (rows + 2 * pad) * tw;
   const int sub = threadIdx.x >> 3, ch4 = (threadIdx.x & 7) * 4;
   constexpr int U = 4, PP = kDwThreads / 8;
   for (int i0 = sub; i0 < total; i0 += U * PP) {
@@ -65,26 +69,28 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_kernel(const float* __re
   const int c = blockIdx.y * kDwCG + lane;
   const int n = blockIdx.z;
   const int y0 = blockIdx.x * band, rows = min(band, h - y0);
-  const int tw = w + 2 * kDwR, th = rows + 2 * kDwR;
+  const int xg = (w + 3) / 4;                            // groups of 4 adjacent outputs per row
+  const int tw = xg * 4 + 2 * kDwR;
   const float* src = in + (long long)n * h * w * C;
-  (void)th;
-  stage_tile(tile, src, C, blockIdx.y * kDwCG, h, w, y0, rows, kDwR);
+  stage_tile(tile, src, C, blockIdx.y * kDwCG, h, w, y0, rows, kDwR, tw);
   float wreg[kDwT];
 #pragma unroll
   for (int k = 0; k < kDwT; ++k) wreg[k] = wt[(long long)c * kDwT + (FLIP ? kDwT - 1 - k : k)];
   const float b = bias ? bias[c] : 0.f;
   __syncthreads();
-  const int xg = (w + 3) / 4;                            // groups of 4 adjacent outputs per row
-  float* dst = out + (long long)n * h * w * C;
-  for (int item = warp; item < rows * xg; item += kDwThreads / 32) {
-    const int y = item / xg, x0 = (item % xg) * 4;
+  float* dst = out + ((long long)n * h + y0) * w * C + c;
+  const int rstride = tw * kDwCG;
+  int y = 0, xi = warp;
+  while (xi >= xg) { xi -= xg; ++y; }
+  while (y < rows) {
+    const int x0 = xi * 4;
     float acc[4] = {b, b, b, b};
+    const float* row = tile + (y * tw + x0) * kDwCG + lane;
 #pragma unroll
-    for (int dy = 0; dy < kDwK; ++dy) {
-      const float* row = tile + ((y + dy) * tw + x0) * kDwCG + lane;
+    for (int dy = 0; dy < kDwK; ++dy, row += rstride) {
       float v[10];
 #pragma unroll
-      for (int j = 0; j < 10; ++j) v[j] = (x0 + j < tw) ? row[j * kDwCG] : 0.f;
+      for (int j = 0; j < 10; ++j) v[j] = row[j * kDwCG];
 #pragma unroll
       for (int dx = 0; dx < kDwK; ++dx) {
         const float ww = wreg[dy * kDwK + dx];
@@ -92,9 +98,12 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_kernel(const float* __re
         for (int o = 0; o < 4; ++o) acc[o] = fmaf(ww, v[o + dx], acc[o]);
       }
     }
+    float* d = dst + ((long long)y * w + x0) * C;
 #pragma unroll
     for (int o = 0; o < 4; ++o)
-      if (x0 + o < w) dst[((long long)(y0 + y) * w + x0 + o) * C + c] = acc[o];
+      if (x0 + o < w) d[(long long)o * C] = acc[o];
+    xi += kDwThreads / 32;
+    while (xi >= xg) { xi -= xg; ++y; }
   }
 }
 
@@ -110,29 +119,33 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_wgrad_kernel(const float
   const int c = blockIdx.y * kDwCG + lane;
   const int n = blockIdx.z;
   const int y0 = blockIdx.x * band, rows = min(band, h - y0);
-  const int tw = w + 2 * kDwR;
+  const int wp = dw_pad(w, 8), tw = wp + 2 * kDwR;
   float* xt = sm;
   float* gt = sm + (size_t)(band + 2 * kDwR) * tw * kDwCG;
-  stage_tile(xt, in + (long long)n * h * w * C, C, blockIdx.y * kDwCG, h, w, y0, rows, kDwR);
-  stage_tile(gt, dout + (long long)n * h * w * C, C, blockIdx.y * kDwCG, h, w, y0, rows, 0);
+  stage_tile(xt, in + (long long)n * h * w * C, C, blockIdx.y * kDwCG, h, w, y0, rows, kDwR, tw);
+  stage_tile(gt, dout + (long long)n * h * w * C, C, blockIdx.y * kDwCG, h, w, y0, rows, 0, wp);
   __syncthreads();
   float acc[kDwT + 1];
 #pragma unroll
   for (int k = 0; k <= kDwT; ++k) acc[k] = 0.f;
-  for (int y = warp; y < rows; y += kDwThreads / 32) {
-    for (int x0 = 0; x0 < w; x0 += 8) {
+  // (row, 8-output chunk) items round-robin over the warps: balanced for any band height
+  const int xc = wp / 8, rstride = tw * kDwCG;
+  for (int item = warp; item < rows * xc; item += kDwThreads / 32) {
+    {
+      const int y = item / xc, x0 = (item - y * xc) * 8;
       float g[8];
+      const float* gr = gt + ((size_t)y * wp + x0) * kDwCG + lane;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        g[j] = (x0 + j < w) ? gt[((size_t)y * w + x0 + j) * kDwCG + lane] : 0.f;
+        g[j] = gr[j * kDwCG];
         acc[kDwT] += g[j];
       }
+      const float* xr = xt + ((size_t)y * tw + x0) * kDwCG + lane;
 #pragma unroll
-      for (int dy = 0; dy < kDwK; ++dy) {
-        const float* xr = xt + ((size_t)(y + dy) * tw + x0) * kDwCG + lane;
+      for (int dy = 0; dy < kDwK; ++dy, xr += rstride) {
         float v[14];
 #pragma unroll
-        for (int j = 0; j < 14; ++j) v[j] = (x0 + j < tw) ? xr[j * kDwCG] : 0.f;
+        for (int j = 0; j < 14; ++j) v[j] = xr[j * kDwCG];
 #pragma unroll
         for (int dx = 0; dx < kDwK; ++dx)
 #pragma unroll
@@ -155,10 +168,11 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_cl_wgrad_kernel(const float
 
 // d w[c][k] = sum over (image, band) partials in order; d bias likewise
 __global__ void dwconv_fold_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ dw, float* __restrict__ db) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C * (kDwT + 1)) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(long long)p * C * (kDwT + 1) + i];
+  __shared__ float sm[kFoldTy][32];
+  const int total = C * (kDwT + 1);
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const float s = fold_parts(part, nparts, total, i, i < total, sm);
+  if (threadIdx.y != 0 || i >= total) return;
   const int c = i / (kDwT + 1), k = i % (kDwT + 1);
   if (k < kDwT) dw[c * kDwT + k] = s;
   else if (db) db[c] = s;
@@ -178,7 +192,7 @@ extern "C" int cor_dwconv7_cl(const float* in, const float* weight, const float*
   COR_REQUIRE(in && weight && out, "cor_dwconv7_cl: null pointer");
   COR_REQUIRE(n > 0 && h > 0 && w > 0 && C > 0 && C % kDwCG == 0, "cor_dwconv7_cl: need C %% 32 == 0 (C=%d)", C);
   const int band = dw_band_rows(h, w, 0);
-  const size_t smem = (size_t)(band + 2 * kDwR) * (w + 2 * kDwR) * kDwCG * sizeof(float);
+  const size_t smem = (size_t)(band + 2 * kDwR) * (dw_pad(w, 4) + 2 * kDwR) * kDwCG * sizeof(float);
   COR_REQUIRE(smem <= 200 * 1024, "cor_dwconv7_cl: map too wide (w=%d)", w);
   const dim3 grid(ceil_div(h, band), C / kDwCG, n);
   cudaStream_t st = as_stream(stream);
@@ -197,7 +211,7 @@ extern "C" int cor_dwconv7_cl_wgrad(const float* in, const float* dout, float* d
   COR_REQUIRE(in && dout && dweight && work, "cor_dwconv7_cl_wgrad: null pointer");
   COR_REQUIRE(n > 0 && h > 0 && w > 0 && C > 0 && C % kDwCG == 0, "cor_dwconv7_cl_wgrad: need C %% 32 == 0 (C=%d)", C);
   const int band = dw_band_rows(h, w, 1);
-  const size_t smem = ((size_t)(band + 2 * kDwR) * (w + 2 * kDwR) + (size_t)band * w) * kDwCG * sizeof(float);
+  const size_t smem = ((size_t)(band + 2 * kDwR) * (dw_pad(w, 8) + 2 * kDwR) + (size_t)band * dw_pad(w, 8)) * kDwCG * sizeof(float);
   COR_REQUIRE(smem <= 220 * 1024, "cor_dwconv7_cl_wgrad: map too wide (w=%d)", w);
   const int bands = ceil_div(h, band);
   const dim3 grid(bands, C / kDwCG, n);
@@ -208,6 +222,6 @@ extern "C" int cor_dwconv7_cl_wgrad(const float* in, const float* dout, float* d
   int rc = check_launch("dwconv_cl_wgrad_kernel");
   if (rc) return rc;
   const int total = C * (kDwT + 1);
-  dwconv_fold_kernel<<<(total + 255) / 256, 256, 0, st>>>(part, n * bands, C, dweight, dbias);
+  dwconv_fold_kernel<<<(total + 31) / 32, dim3(32, kFoldTy), 0, st>>>(part, n * bands, C, dweight, dbias);
   return check_launch("dwconv_fold_kernel");
 }

@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_fwd_kernel(const float*
 }
 
 // dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * act'(.) * w;  dw_part / db_part [gridDim.x][C]
-template <int PL>
-__global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+template <typename TD, int PL>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const TD* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ w, const float* __restrict__ b,
                                                                     const float* __restrict__ stats, long long rows, int C, int act,
                                                                     long long rows_per_cta, float* __restrict__ dx,
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const float*
       g[i] = xh[i] = 0.f;
       if (c < C) {
         xh[i] = (x[row * C + c] - mean) * rstd;
-        float d = dy[row * C + c];
+        float d = to_f<TD>(dy[row * C + c]);
         if (act == COR_ACT_GELU) d *= gelu_grad(xh[i] * w[c] + b[c]);
         aw[i] = fmaf(d, xh[i], aw[i]);
         ab[i] += d;
@@ -113,18 +113,17 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const float*
   }
 }
 
+// grid = (ceil(C / 32), 2): y = 0 folds d weight, y = 1 d bias
 __global__ void ln_fold_kernel(const float* __restrict__ dw_part, const float* __restrict__ db_part, int nparts, int C,
                                float* __restrict__ dw, float* __restrict__ db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float sw = 0.f, sb = 0.f;
-  for (int k = 0; k < nparts; ++k) { sw += dw_part[(long long)k * C + c]; sb += db_part[(long long)k * C + c]; }
-  dw[c] = sw;
-  db[c] = sb;
+  __shared__ float sm[kFoldTy][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const float t = fold_parts(blockIdx.y ? db_part : dw_part, nparts, C, c, c < C, sm);
+  if (threadIdx.y == 0 && c < C) (blockIdx.y ? db : dw)[c] = t;
 }
 
 static int ln_parts(long long rows) {
-  long long p = (rows + kLnWarps * 16 - 1) / (kLnWarps * 16);      // >= 16 rows per warp
+  long long p = (rows + kLnWarps * 4 - 1) / (kLnWarps * 4);        // >= 4 rows per warp
   const long long cap = (long long)sm_count() * 4;
   if (p > cap) p = cap;
   return (int)(p < 1 ? 1 : p);
@@ -151,7 +150,7 @@ extern "C" int cor_ln_rows_fwd(const float* x, const float* weight, const float*
   return check_launch("ln_rows_fwd_kernel");
 }
 
-extern "C" int cor_ln_rows_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* stats,
+extern "C" int cor_ln_rows_bwd(const void* dy, int dy_dtype, const float* x, const float* weight, const float* bias, const float* stats,
                                long long rows, int C, int act, float* dx, float* dweight, float* dbias, void* work, cor_stream_t stream) {
   COR_REQUIRE(dy && x && weight && bias && stats && dx && dweight && dbias && work, "cor_ln_rows_bwd: null pointer");
   COR_REQUIRE(rows > 0 && C > 0 && C <= 32 * kLnMaxPerLane, "cor_ln_rows_bwd: need 0 < C <= %d (C=%d)", 32 * kLnMaxPerLane, C);
@@ -161,15 +160,18 @@ extern "C" int cor_ln_rows_bwd(const float* dy, const float* x, const float* wei
   float* dbp = dwp + (size_t)parts * C;
   cudaStream_t st = as_stream(stream);
   const size_t smem = (size_t)2 * kLnWarps * C * sizeof(float);
-#define COR_LN_B(PL)                                                                                                              \
+  COR_REQUIRE(dy_dtype == COR_F32 || dy_dtype == COR_BF16, "cor_ln_rows_bwd: gradient dtype %d", dy_dtype);
+#define COR_LN_B(TD, PL)                                                                                                          \
   do {                                                                                                                            \
-    COR_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
-    ln_rows_bwd_kernel<PL><<<parts, kLnWarps * 32, smem, st>>>(dy, x, weight, bias, stats, rows, C, act, per, dx, dwp, dbp);      \
+    COR_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel<TD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    ln_rows_bwd_kernel<TD, PL><<<parts, kLnWarps * 32, smem, st>>>(reinterpret_cast<const TD*>(dy), x, weight, bias, stats, rows, \
+                                                                   C, act, per, dx, dwp, dbp);                                    \
   } while (0)
-  if (C <= 256) COR_LN_B(8); else if (C <= 512) COR_LN_B(16); else COR_LN_B(32);
+  if (dy_dtype == COR_F32) { if (C <= 256) COR_LN_B(float, 8); else if (C <= 512) COR_LN_B(float, 16); else COR_LN_B(float, 32); }
+  else { if (C <= 256) COR_LN_B(bf16, 8); else if (C <= 512) COR_LN_B(bf16, 16); else COR_LN_B(bf16, 32); }
 #undef COR_LN_B
   int rc = check_launch("ln_rows_bwd_kernel");
   if (rc) return rc;
-  ln_fold_kernel<<<(C + 127) / 128, 128, 0, st>>>(dwp, dbp, parts, C, dweight, dbias);
+  ln_fold_kernel<<<dim3((C + 31) / 32, 2), dim3(32, kFoldTy), 0, st>>>(dwp, dbp, parts, C, dweight, dbias);
   return check_launch("ln_fold_kernel");
 }

@@ -322,10 +322,9 @@ static int nce_launch(const void* X, const void* Y, int Nx, int Ny, int Nq, int 
 using namespace cor;
 
 extern "C" size_t cor_infonce_bwd_umma_work_bytes(int Nq, int Nr, int D) {
-  // split-over-regions partials of dQ (dR needs none unless there are fewer region tiles than SMs)
-  const int qt = ceil_div(Nq, kNbM), rt = ceil_div(Nr, kNbN);
-  const size_t sq = (size_t)nce_splits(qt, rt) * Nq * D * sizeof(float);
-  const size_t sr = (size_t)nce_splits(rt, qt) * Nr * D * sizeof(float);
+  // the two launches' partials (nce_launch: X tiles of kNbM rows, Y tiles of kNbN rows), one after the other in the same buffer
+  const size_t sq = (size_t)nce_splits(ceil_div(Nq, kNbM), ceil_div(Nr, kNbN)) * Nq * D * sizeof(float);      // mode 0: X = queries
+  const size_t sr = (size_t)nce_splits(ceil_div(Nr, kNbM), ceil_div(Nq, kNbN)) * Nr * D * sizeof(float);      // mode 1: X = regions
   return (sq > sr ? sq : sr) + 256;
 }
 

@@ -83,7 +83,7 @@ def _weight_bf16(w: torch.Tensor) -> torch.Tensor:
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, drop_mask, x2, colscale, residual):
+    def forward(ctx, x, weight, bias, act, drop_mask, x2, colscale, residual, out_bf16):
         dev = L.require_cuda(x, weight, bias, drop_mask, x2, colscale, residual)
         rows = x.shape[0]
         x16 = cast_bf16(x, x2) if x.dtype != torch.bfloat16 or x2 is not None else x.contiguous()   # torch.cat((x, x2), -1) fused with the cast
@@ -97,10 +97,11 @@ class _LinearFn(torch.autograd.Function):
         m32 = drop_mask.float().contiguous() if drop_mask is not None else None
         cs = colscale.float().contiguous() if colscale is not None else None
         want_pre = act == ACT_GELU or (cs is not None and colscale.requires_grad)
-        out = gemm(x16, w16, rows, N, K, bias=b32, act=act, emul=m32, colscale=cs, residual=residual, want_pre=want_pre)
+        out = gemm(x16, w16, rows, N, K, bias=b32, act=act, emul=m32, colscale=cs, residual=residual, want_pre=want_pre,
+                   out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
         y, pre = out if want_pre else (out, None)
         # relu / sigmoid differentiate through the stored OUTPUT (only used when there is neither scale nor residual)
-        ctx.save_for_backward(x16, w16, y if act in (ACT_RELU, ACT_SIGMOID) else None, pre, m32, cs)
+        ctx.save_for_backward(x16, w16, (y.float() if y.dtype != torch.float32 else y) if act in (ACT_RELU, ACT_SIGMOID) else None, pre, m32, cs)
         ctx.cfg = (act, x.shape[1], x.requires_grad, x2 is not None and x2.requires_grad, weight.requires_grad,
                    bias is not None and bias.requires_grad, colscale is not None and colscale.requires_grad,
                    residual is not None and residual.requires_grad, x.dtype, weight.dtype, tuple(weight.shape), rows, N)
@@ -112,31 +113,34 @@ class _LinearFn(torch.autograd.Function):
         act, c0, need_x, need_x2, need_w, need_b, need_cs, need_res, xdt, wdt, wshape, rows, N = ctx.cfg
         dev = x16.device
         K = x16.shape[1]
-        gy = gy.float().contiguous()
+        gy = (gy if gy.dtype in (torch.float32, torch.bfloat16) else gy.float()).contiguous()
         dz = torch.empty((rows, N), dtype=torch.bfloat16, device=dev)
         db = torch.empty((N,), dtype=torch.float32, device=dev) if need_b else None
         dcs = torch.empty((N,), dtype=torch.float32, device=dev) if need_cs else None
         work = ops._work(L.load().cor_act_bwd_work_bytes(rows, N), dev) if (need_b or need_cs) else None
-        ops._call("cor_act_bwd", dev, ops.ptr(gy), ops.ptr(y), ops.ptr(pre), ops.ptr(m32), ops.ptr(cs), int(act), ops._ll(rows), N,
+        ops._call("cor_act_bwd", dev, ops.ptr(gy), L.dtype_code(gy), ops.ptr(y), ops.ptr(pre), ops.ptr(m32), ops.ptr(cs), int(act), ops._ll(rows), N,
                   ops.ptr(dz), ops.ptr(db), ops.ptr(dcs), ops.ptr(work))
         gx = gx2 = gw = None
         if need_x or need_x2:
-            g_in = gemm(dz, w16, rows, K, N, b_mn=True)                   # dX = dZ W : W [N, K] read as the MN-major B (k = out features)
+            # dX = dZ W : W [N, K] read as the MN-major B (k = out features); a bf16 input gets its gradient in bf16 straight
+            # from the epilogue
+            g_in = gemm(dz, w16, rows, K, N, b_mn=True, out_dtype=torch.bfloat16 if (xdt == torch.bfloat16 and c0 == K) else torch.float32)
             gx = (g_in[:, :c0] if c0 != K else g_in).to(xdt) if need_x else None
             gx2 = g_in[:, c0:].to(xdt) if need_x2 else None
         if need_w:
             gw = gemm(dz, x16, N, K, rows, a_mn=True, b_mn=True).view(wshape).to(wdt)   # dW = dZ^T X : both operands MN-major (k = rows)
-        return gx, gw, db, None, None, gx2, dcs, (gy if need_res else None)
+        return gx, gw, db, None, None, gx2, dcs, ((gy if gy.dtype == torch.float32 else gy.float()) if need_res else None), None
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
            drop_mask: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None, colscale: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+           residual: Optional[torch.Tensor] = None, out_bf16: bool = False) -> torch.Tensor:
     """``residual + colscale * drop_mask * act(cat(x, x2) @ weight.T + bias)`` -> f32 [rows, out_features]; x [rows, in] f32
     or bf16 (any leading shape is flattened by the caller).  ``drop_mask`` holds 0 or 1/(1-p) per element (what
     ``F.dropout`` multiplies by); ``colscale`` [out] and ``residual`` [rows, out] are ConvNeXt's layer scale and skip
-    connection (mask_adapter.py:215-221), fused into the same GEMM epilogue."""
-    return _LinearFn.apply(x, weight, bias, _ACTS[act], drop_mask, x2, colscale, residual)
+    connection (mask_adapter.py:215-221), fused into the same GEMM epilogue.  ``out_bf16`` writes the result in bf16 (the next
+    GEMM's A operand: no fp32 round trip of a wide hidden activation)."""
+    return _LinearFn.apply(x, weight, bias, _ACTS[act], drop_mask, x2, colscale, residual, bool(out_bf16))
 
 
 class _LnRowsFn(torch.autograd.Function):
@@ -160,12 +164,12 @@ class _LnRowsFn(torch.autograd.Function):
         act, wdt = ctx.cfg
         dev = x.device
         rows, Cc = x.shape
-        gy = gy.float().contiguous()
+        gy = (gy if gy.dtype in (torch.float32, torch.bfloat16) else gy.float()).contiguous()
         dx = torch.empty_like(x)
         dw = torch.empty((Cc,), dtype=torch.float32, device=dev)
         db = torch.empty((Cc,), dtype=torch.float32, device=dev)
         work = ops._work(L.load().cor_ln_rows_work_bytes(rows, Cc), dev)
-        ops._call("cor_ln_rows_bwd", dev, ops.ptr(gy), ops.ptr(x), ops.ptr(w), ops.ptr(b), ops.ptr(stats), ops._ll(rows), Cc, act, ops.ptr(dx),
+        ops._call("cor_ln_rows_bwd", dev, ops.ptr(gy), L.dtype_code(gy), ops.ptr(x), ops.ptr(w), ops.ptr(b), ops.ptr(stats), ops._ll(rows), Cc, act, ops.ptr(dx),
                   ops.ptr(dw), ops.ptr(db), ops.ptr(work))
         return dx, dw.to(wdt), db.to(wdt), None, None, None
 

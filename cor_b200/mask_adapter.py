@@ -138,7 +138,7 @@ def _convnext_rows(blk, y: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor
         img = y.view(n, h, w, c).permute(0, 3, 1, 2)                   # NCHW shape, channels_last strides: no copy
         t = _rows(F.conv2d(img, blk.dwconv.weight.float(), blk.dwconv.bias.float(), padding=blk.dwconv.padding, groups=c))
     t = ln_rows(t, blk.norm.weight, blk.norm.bias, blk.norm.eps, None, out_bf16=True)
-    hdn = linear(t, blk.pwconv1.weight, blk.pwconv1.bias, "gelu")
+    hdn = linear(t, blk.pwconv1.weight, blk.pwconv1.bias, "gelu", out_bf16=True)       # [rows, 4C] stays bf16 between the two GEMMs
     # gamma * pwconv2(.) + input: layer scale and skip connection in the GEMM epilogue
     return linear(hdn, blk.pwconv2.weight, blk.pwconv2.bias, None, None, None, blk.gamma, y)
 

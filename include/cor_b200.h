@@ -290,7 +290,8 @@ int cor_gemm_bf16(const void* A, int a_mn, long long a_rows_total, long long a_b
  *                work: cor_act_bwd_work_bytes(M, N) bytes when db or dcolscale is requested. */
 int cor_cast_cat_bf16(const float* a, int c0, const float* b, int c1, long long rows, void* out_bf16, cor_stream_t stream);
 size_t cor_act_bwd_work_bytes(long long M, int N);
-int cor_act_bwd(const float* dy, const float* y_f32, const void* pre_bf16, const float* emul, const float* colscale, int act,
+int cor_act_bwd(const void* dy, int dy_dtype /* f32 or bf16 */, const float* y_f32, const void* pre_bf16, const float* emul,
+                const float* colscale, int act,
                 long long M, int N, void* dz_bf16, float* db, float* dcolscale, void* work, cor_stream_t stream);
 
 /* Row-wise LayerNorm (+ optional GELU) over channels-last rows, forward and backward (csrc/ln_rows.cu): the norms of the
@@ -300,7 +301,7 @@ int cor_act_bwd(const float* dy, const float* y_f32, const void* pre_bf16, const
 size_t cor_ln_rows_work_bytes(long long rows, int C);
 int cor_ln_rows_fwd(const float* x, const float* weight, const float* bias, long long rows, int C, float eps, int act,
                     void* y, int y_dtype, float* stats, cor_stream_t stream);
-int cor_ln_rows_bwd(const float* dy, const float* x, const float* weight, const float* bias, const float* stats,
+int cor_ln_rows_bwd(const void* dy, int dy_dtype /* f32 or bf16 */, const float* x, const float* weight, const float* bias, const float* stats,
                     long long rows, int C, int act, float* dx, float* dweight, float* dbias, void* work, cor_stream_t stream);
 
 /* Depth-wise 7x7 convolution (padding 3, stride 1) on channels-last maps [n][h][w][C] f32 (csrc/dwconv.cu): the spatial
