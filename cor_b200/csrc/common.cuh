@@ -83,24 +83,55 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
-// Sum over `nparts` partial rows of column c (part[k * ld + c]) by a (32, kFoldTy) thread block: thread row ty takes
-// k = ty, ty + kFoldTy, ... with four independent accumulators (loads pipeline; a single serial chain over ~2000 partials
+// ---- GELU (erf form, torch nn.GELU() default) on the SFU, branch-free --------------------------------------------------
+// 1 - Phi(|x|) = 0.5 erfc(|x| / sqrt 2) through Abramowitz-Stegun 7.1.26: erfc(z) = (a1 t + .. + a5 t^5) exp(-z^2),
+// t = 1 / (1 + p z), |error| <= 1.5e-7 absolute.  MUFU.RCP + MUFU.EX2 + 9 FMA-pipe instructions; the 0.5 is folded into
+// the coefficients and exp(-z^2) = 2^(-x^2 * log2(e) / 2).  `e` returns that exponential (the Gaussian of gelu').
+// Used where the result is rounded to bf16 anyway (GEMM epilogue with bf16 output, activation backward): libdevice's
+// erff + expf + IEEE reciprocal cost 45 instructions and a branch per element and made the epilogue the bottleneck.
+__device__ __forceinline__ float gelu_tail(float x, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, ee;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ee) : "f"(x * x * -0.72134752044448170f));
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  e = ee;
+  return p * t * ee;                                          // 1 - Phi(|x|)
+}
+__device__ __forceinline__ float gelu_cdf_fast(float x, float& e) {
+  const float q = gelu_tail(x, e);
+  return 0.5f + copysignf(0.5f - q, x);                      // Phi(x) = 1 - q (x >= 0), q (x < 0)
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e;
+  return x * gelu_cdf_fast(x, e);
+}
+// d gelu / dx = Phi(x) + x phi(x), phi(x) = exp(-x^2 / 2) / sqrt(2 pi): one exponential for both terms
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float e;
+  const float cdf = gelu_cdf_fast(x, e);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+// Sum over `nparts` partial rows of column c (part[k * ld + c]) by a (32, kFoldTy = 32) thread block: thread row ty takes
+// k = ty, ty + kFoldTy, ... with eight independent accumulators (loads pipeline; a single serial chain over ~2000 partials
 // cost 100 us), then the kFoldTy row sums are added in fixed order.  Deterministic; the total is returned to ty == 0.
-constexpr int kFoldTy = 16;
+constexpr int kFoldTy = 32;
 __device__ __forceinline__ float fold_parts(const float* __restrict__ part, int nparts, long long ld, long long c, bool ok,
                                             float (*sm)[32]) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (ok) {
     int k = threadIdx.y;
-    for (; k + 3 * kFoldTy < nparts; k += 4 * kFoldTy) {
-      s0 += part[(long long)k * ld + c];
-      s1 += part[(long long)(k + kFoldTy) * ld + c];
-      s2 += part[(long long)(k + 2 * kFoldTy) * ld + c];
-      s3 += part[(long long)(k + 3 * kFoldTy) * ld + c];
+    for (; k + 7 * kFoldTy < nparts; k += 8 * kFoldTy) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += part[(long long)(k + u * kFoldTy) * ld + c];
     }
-    for (; k < nparts; k += kFoldTy) s0 += part[(long long)k * ld + c];
+    for (; k < nparts; k += kFoldTy) s[0] += part[(long long)k * ld + c];
   }
-  sm[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+  sm[threadIdx.y][threadIdx.x] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
   __syncthreads();
   float t = 0.f;
   if (threadIdx.y == 0) {

@@ -38,8 +38,6 @@ __global__ void __launch_bounds__(256) cast_cat_bf16_vec_kernel(const float* __r
 // y = the activation's OUTPUT before mask / scale (relu, sigmoid) or pre = its pre-activation (gelu; also the un-scaled
 // linear output when a column scale is used), saved bf16 by the GEMM epilogue.  grid = (column blocks, row chunks): a thread
 // walks its column over the chunk's rows (coalesced across the warp), per-chunk partial sums are folded in chunk order.
-__device__ __forceinline__ float gelu_grad_fast(float x);
-
 template <typename TD>
 __global__ void __launch_bounds__(128) act_bwd_kernel(const TD* __restrict__ dy, const float* __restrict__ y_f32,
                                                      const bf16* __restrict__ pre_bf16, const float* __restrict__ emul,
@@ -72,20 +70,6 @@ __global__ void __launch_bounds__(128) act_bwd_kernel(const TD* __restrict__ dy,
   if (dcs_part) dcs_part[(long long)blockIdx.y * N + n] = accs;
 }
 
-// d gelu(x) / dx = Phi(x) + x phi(x) with ONE exponential: phi's exp(-x^2/2) is also the exponential of erf's
-// Abramowitz-Stegun 7.1.26 form (|error| <= 1.5e-7 on erf; x itself is the bf16-rounded saved pre-activation).
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float e = __expf(-z * z);
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float q = 0.5f * p * t * e;                           // 1 - Phi(|x|)
-  return (x >= 0.f ? 1.f - q : q) + x * 0.3989422804014327f * e;
-}
-
 template <typename TD>
 __device__ __forceinline__ void load4(const TD* p, float (&v)[4]);
 template <>
@@ -100,7 +84,7 @@ __device__ __forceinline__ void load4<bf16>(const bf16* p, float (&v)[4]) {
   v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
 }
 
-// The same with 4 adjacent columns per thread and two rows in flight (N % 4 == 0, 16-byte aligned tensors): 128-bit /
+// The same with 4 adjacent columns per thread and four rows in flight (N % 4 == 0, 16-byte aligned tensors): 128-bit /
 // 64-bit accesses, the activation a template parameter.  Per-column sums are per thread, so the summation order over rows
 // is the scalar kernel's.
 template <typename TD, int ACT>
@@ -114,7 +98,7 @@ __global__ void __launch_bounds__(128) act_bwd_vec_kernel(const TD* __restrict__
   float cs[4] = {1.f, 1.f, 1.f, 1.f};
   if (colscale) load4<float>(colscale + n, cs);
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
-  constexpr int U = 2;
+  constexpr int U = 4;
   for (long long m = m0; m < m1; m += U) {
     float g[U][4], x[U][4], e[U][4];
 #pragma unroll

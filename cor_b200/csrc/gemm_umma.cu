@@ -18,7 +18,9 @@
 //   v *= colscale[n]; v += residual[m][n]; C = v
 // Split-K (gridDim.y > 1, for the weight-gradient GEMMs whose K is the row count) writes raw fp32 partials and a fold
 // kernel applies the epilogue in fixed order (deterministic).
-// Warp roles (320 threads): 0..7 epilogue (lane quarter w % 4, column half w / 4), 8 TMA producer, 9 MMA issuer.
+// Warp roles (576 threads): 0..15 epilogue (TMEM lane quarter w % 4, 32-column chunk w / 4 of the 128-column tile -- four
+// epilogue warps per scheduler: with two the short-K GEMMs, which are epilogue-bound, filled 40 % of the issue slots),
+// 16 TMA producer, 17 MMA issuer.
 #include "umma.cuh"
 
 namespace cor {
@@ -27,8 +29,9 @@ using namespace umma;
 
 constexpr int kGmBM = 128, kGmBN = 128, kGmBK = 64;
 constexpr int kGmTile = 128 * 64 * 2;            // 16 KB: one operand stage
-constexpr int kGmStages = 6;
-constexpr int kGmTmaWarp = 8, kGmMmaWarp = 9;
+constexpr int kGmStages = 5;
+constexpr int kGmStgPitch = 80, kGmStgBytes = 32 * kGmStgPitch;      // per-warp transpose block: 32 rows x (64 B + 16 B pad)
+constexpr int kGmEpiWarps = 16, kGmTmaWarp = 16, kGmMmaWarp = 17, kGmThreads = 32 * (kGmEpiWarps + 2);
 
 struct GemmSmemTail {
   uint64_t full[kGmStages], empty[kGmStages], acc_full[2], acc_empty[2];
@@ -64,18 +67,8 @@ __device__ __forceinline__ float gemm_act(float v, int act) {
 
 // The activation over a 32-column chunk with the switch OUTSIDE the unrolled loop: one branch per chunk, 32 independent
 // evaluations in flight (a per-element switch compiled to an indirect branch per element and serialised the epilogue).
-// ``fast_gelu`` (bf16 outputs only): Phi(x) through erf's Abramowitz-Stegun 7.1.26 form, |error| <= 1.5e-7 absolute on erf,
-// far below the bf16 rounding of the stored value; ~half the instructions of erff.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float q = 0.5f * p * t * __expf(-z * z);              // 1 - Phi(|x|)
-  return x * (x >= 0.f ? 1.f - q : q);
-}
+// ``fast_gelu`` (bf16 outputs only): gelu_fast of common.cuh (SFU form, |error| <= 1.5e-7 absolute on Phi, far below the
+// bf16 rounding of the stored value).
 __device__ __forceinline__ void gemm_act32(float (&o)[32], int act, bool fast_gelu) {
   switch (act) {
     case COR_ACT_RELU:
@@ -109,12 +102,56 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t smem_addr) 
   return d;
 }
 
-__global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+// The epilogue thread owns one ROW of the tile (TMEM lane), so a direct 16-byte store per lane touches 32 different rows:
+// 32 half-written sectors per instruction.  These two primitives transpose 32 rows x 64 bytes through a per-warp shared
+// block so that every global access instruction covers 8 rows x 64 contiguous bytes (16 whole sectors): lane r writes its
+// row (pitch 80 B: the eight lanes of a phase hit eight different 16-byte bank groups), then lane l moves chunk l / 8 of row
+// 8 it + l % 8.  Rows >= rows_valid are skipped (ragged M).  All 32 lanes must call.
+__device__ __forceinline__ void warp_rows_store64(uint8_t* stg, int lane, const uint4 (&c)[4], uint8_t* gbase, long long pitch, int rows_valid) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + lane * kGmStgPitch + j * 16) = c[j];
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane & 7), ch = lane >> 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + r * kGmStgPitch + ch * 16);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(gbase + r * pitch + ch * 16) = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_rows_load64(uint8_t* stg, int lane, uint4 (&c)[4], const uint8_t* gbase, long long pitch, int rows_valid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = it * 8 + (lane & 7), ch = lane >> 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) v = *reinterpret_cast<const uint4*>(gbase + r * pitch + ch * 16);
+    *reinterpret_cast<uint4*>(stg + r * kGmStgPitch + ch * 16) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) c[j] = *reinterpret_cast<const uint4*>(stg + lane * kGmStgPitch + j * 16);
+  __syncwarp();
+}
+__device__ __forceinline__ void pack_bf16_16(const float* o, uint4 (&c)[4]) {      // 32 floats -> 64 bytes
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      __nv_bfloat162 pk = __floats2bfloat162_rn(o[8 * j + 2 * q], o[8 * j + 2 * q + 1]);
+      w[q] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    c[j] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kGmThreads, 1) gemm_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                            GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(base + (size_t)kGmStages * 2 * kGmTile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* stg = reinterpret_cast<uint8_t*>(tail) + ((sizeof(GemmSmemTail) + 15) & ~(size_t)15) + (size_t)(warp < kGmEpiWarps ? warp : 0) * kGmStgBytes;
   const int mt = (g.M + kGmBM - 1) / kGmBM, nt = (g.N + kGmBN - 1) / kGmBN;
   const int ntiles = mt * nt * g.batch;
   const int nkb_all = (g.K + kGmBK - 1) / kGmBK;
@@ -126,7 +163,7 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int i = 0; i < kGmStages; ++i) { mbar_init(&tail->full[i], 1); mbar_init(&tail->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tail->acc_full[i], 1); mbar_init(&tail->acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tail->acc_full[i], 1); mbar_init(&tail->acc_empty[i], kGmEpiWarps); }
     fence_barrier_init();
   }
   if (warp == kGmMmaWarp) tmem_alloc(&tail->tmem_base, 256);
@@ -194,44 +231,49 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
       __syncwarp();
     }
   } else {
-    const int qd = warp & 3, half = warp >> 2;
+    const int qd = warp & 3, colq = warp >> 2;
     int i = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++i) {
       const int buf = i & 1;
       const int b = t / (mt * nt), r = t % (mt * nt);
       const int m = (r / nt) * kGmBM + qd * 32 + lane;
-      const int n0 = (r % nt) * kGmBN + half * 64;
+      const int n0 = (r % nt) * kGmBN + colq * 32;
       const bool mok = m < g.M;
       if (nkb > 0) {
         mbar_wait(&tail->acc_full[buf], (i >> 1) & 1);
         tc_fence_after();
       }
-      uint32_t va[32], vb[32];
+      uint32_t va[32];
       if (nkb > 0) {
-        const uint32_t taddr = tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * kGmBN + half * 64);
-        tmem_ld_32(taddr, va);
-        tmem_ld_32(taddr + 32u, vb);
+        tmem_ld_32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * kGmBN + colq * 32), va);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) va[j] = vb[j] = 0u;
+        for (int j = 0; j < 32; ++j) va[j] = 0u;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0 && nkb > 0) mbar_arrive(&tail->acc_empty[buf]);
-      if (!mok) continue;
       const long long row = (long long)b * g.M + m;
+      const int mw0 = (r / nt) * kGmBM + qd * 32;                  // first row of this warp's 32
+      const int rows_valid = g.M - mw0;                            // <= 0: nothing of this warp's rows exists
+      const long long roww0 = (long long)b * g.M + mw0;
       auto emit = [&](uint32_t (&v)[32], int nb) {
         if (nb >= g.N) return;
+        const bool al16 = ((reinterpret_cast<uintptr_t>(g.C) | reinterpret_cast<uintptr_t>(g.pre) | reinterpret_cast<uintptr_t>(g.residual) |
+                            reinterpret_cast<uintptr_t>(g.emul) | reinterpret_cast<uintptr_t>(g.part)) & 15) == 0;
         if (g.ksplit > 1) {
           float* dst = g.part + (((long long)ks * g.batch + b) * g.M + m) * g.N + nb;
-          const bool vec = (g.N % 4 == 0) && nb + 32 <= g.N;
-          if (vec) {
+          if ((g.N % 4 == 0) && nb + 32 <= g.N && al16) {         // warp-uniform: all lanes take the transposing store
+            uint8_t* gb = reinterpret_cast<uint8_t*>(g.part + (((long long)ks * g.batch + b) * g.M + mw0) * g.N + nb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-          } else {
+            for (int hh = 0; hh < 2; ++hh) {
+              uint4 c[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) c[j] = make_uint4(v[16 * hh + 4 * j], v[16 * hh + 4 * j + 1], v[16 * hh + 4 * j + 2], v[16 * hh + 4 * j + 3]);
+              warp_rows_store64(stg, lane, c, gb + hh * 64, (long long)g.N * 4, rows_valid);
+            }
+          } else if (mok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (nb + j < g.N) dst[j] = __uint_as_float(v[j]);
@@ -239,9 +281,10 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
           return;
         }
         float o[32];
-        const bool fast = nb + 32 <= g.N && g.N % 8 == 0 && g.ldc % 8 == 0 && (!g.residual || g.ldr % 8 == 0);
+        const bool fast = nb + 32 <= g.N && g.N % 8 == 0 && g.ldc % 8 == 0 && (!g.residual || g.ldr % 8 == 0) && al16;
         if (fast) {
-          // whole 32-column chunk, 16-byte aligned rows: every per-column / per-element operand moves as 128-bit vectors
+          // whole 32-column chunk, 16-byte aligned rows (warp-uniform): per-column operands as 128-bit vectors, per-element
+          // operands and results through the transposing 64-byte row moves
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * g.alpha;
           if (g.bias) {
@@ -252,25 +295,21 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
             }
           }
           if (g.pre) {
-            uint4* dstp = reinterpret_cast<uint4*>(g.pre + row * g.ldc + nb);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                __nv_bfloat162 pk = __floats2bfloat162_rn(o[8 * j + 2 * q], o[8 * j + 2 * q + 1]);
-                w[q] = *reinterpret_cast<uint32_t*>(&pk);
-              }
-              dstp[j] = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            uint4 c[4];
+            pack_bf16_16(o, c);
+            warp_rows_store64(stg, lane, c, reinterpret_cast<uint8_t*>(g.pre + roww0 * g.ldc + nb), g.ldc * 2, rows_valid);
           }
           gemm_act32(o, g.act, g.c_bf16 != 0);
           if (g.emul) {
-            const float4* e = reinterpret_cast<const float4*>(g.emul + row * g.N + nb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = e[j];
-              o[4 * j] *= t.x; o[4 * j + 1] *= t.y; o[4 * j + 2] *= t.z; o[4 * j + 3] *= t.w;
+            for (int hh = 0; hh < 2; ++hh) {
+              uint4 c[4];
+              warp_rows_load64(stg, lane, c, reinterpret_cast<const uint8_t*>(g.emul + roww0 * g.N + nb) + hh * 64, (long long)g.N * 4, rows_valid);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                o[16 * hh + 4 * j] *= __uint_as_float(c[j].x); o[16 * hh + 4 * j + 1] *= __uint_as_float(c[j].y);
+                o[16 * hh + 4 * j + 2] *= __uint_as_float(c[j].z); o[16 * hh + 4 * j + 3] *= __uint_as_float(c[j].w);
+              }
             }
           }
           if (g.colscale) {
@@ -282,23 +321,49 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
           }
           if (g.residual) {
             if (g.res_bf16) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(g.residual) + row * g.ldr + nb);
+              uint4 c[4];
+              warp_rows_load64(stg, lane, c, reinterpret_cast<const uint8_t*>(reinterpret_cast<const bf16*>(g.residual) + roww0 * g.ldr + nb),
+                               g.ldr * 2, rows_valid);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 t = r4[j];
+                const uint4 t = c[j];
                 o[8 * j] += bf16lo(t.x); o[8 * j + 1] += bf16hi(t.x); o[8 * j + 2] += bf16lo(t.y); o[8 * j + 3] += bf16hi(t.y);
                 o[8 * j + 4] += bf16lo(t.z); o[8 * j + 5] += bf16hi(t.z); o[8 * j + 6] += bf16lo(t.w); o[8 * j + 7] += bf16hi(t.w);
               }
             } else {
-              const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.residual) + row * g.ldr + nb);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 t = r4[j];
-                o[4 * j] += t.x; o[4 * j + 1] += t.y; o[4 * j + 2] += t.z; o[4 * j + 3] += t.w;
+              for (int hh = 0; hh < 2; ++hh) {
+                uint4 c[4];
+                warp_rows_load64(stg, lane, c, reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(g.residual) + roww0 * g.ldr + nb) + hh * 64,
+                                 g.ldr * 4, rows_valid);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  o[16 * hh + 4 * j] += __uint_as_float(c[j].x); o[16 * hh + 4 * j + 1] += __uint_as_float(c[j].y);
+                  o[16 * hh + 4 * j + 2] += __uint_as_float(c[j].z); o[16 * hh + 4 * j + 3] += __uint_as_float(c[j].w);
+                }
               }
             }
           }
-        } else {
+          if (g.c_bf16) {
+            uint4 c[4];
+            pack_bf16_16(o, c);
+            warp_rows_store64(stg, lane, c, reinterpret_cast<uint8_t*>(reinterpret_cast<bf16*>(g.C) + roww0 * g.ldc + nb), g.ldc * 2, rows_valid);
+          } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint4 c[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                c[j] = make_uint4(__float_as_uint(o[16 * hh + 4 * j]), __float_as_uint(o[16 * hh + 4 * j + 1]), __float_as_uint(o[16 * hh + 4 * j + 2]),
+                                  __float_as_uint(o[16 * hh + 4 * j + 3]));
+              warp_rows_store64(stg, lane, c, reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(g.C) + roww0 * g.ldc + nb) + hh * 64, g.ldc * 4,
+                                rows_valid);
+            }
+          }
+          return;
+        }
+        if (!mok) return;
+        {                                                           // ragged / unaligned chunk: per-thread, per-element
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = nb + j;
@@ -358,7 +423,6 @@ __global__ void __launch_bounds__(320, 1) gemm_umma_kernel(const __grid_constant
         }
       };
       emit(va, n0);
-      emit(vb, n0 + 32);
     }
   }
   tc_fence_before();
@@ -439,10 +503,10 @@ extern "C" int cor_gemm_bf16(const void* A, int a_mn, long long a_rows_total, lo
   int gx = sm_count() / g.ksplit;
   if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
-  const size_t smem = (size_t)kGmStages * 2 * kGmTile + sizeof(GemmSmemTail) + 1024;
+  const size_t smem = (size_t)kGmStages * 2 * kGmTile + sizeof(GemmSmemTail) + 16 + (size_t)kGmEpiWarps * kGmStgBytes + 1024;
   COR_CUDA(cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = as_stream(stream);
-  gemm_umma_kernel<<<dim3(gx, g.ksplit), 320, smem, st>>>(tmA, tmB, g);
+  gemm_umma_kernel<<<dim3(gx, g.ksplit), kGmThreads, smem, st>>>(tmA, tmB, g);
   rc = check_launch("gemm_umma_kernel");
   if (rc || g.ksplit == 1) return rc;
   const long long total = (long long)batch * M * N;

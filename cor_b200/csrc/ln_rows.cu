@@ -19,7 +19,39 @@ __device__ __forceinline__ float gelu_grad(float x) {
   return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
-template <typename TO, int PL>      // PL = values per lane: C <= 32 * PL
+// VEC adjacent columns per lane and load (4 when C % 4 == 0: 128-bit fp32 / 64-bit bf16 accesses; else 1)
+template <typename T, int VEC>
+__device__ __forceinline__ void ldv(const T* p, float* v);
+template <>
+__device__ __forceinline__ void ldv<float, 1>(const float* p, float* v) { v[0] = *p; }
+template <>
+__device__ __forceinline__ void ldv<bf16, 1>(const bf16* p, float* v) { v[0] = __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ void ldv<float, 4>(const float* p, float* v) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void ldv<bf16, 4>(const bf16* p, float* v) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void stv(T* p, const float* v);
+template <>
+__device__ __forceinline__ void stv<float, 1>(float* p, const float* v) { *p = v[0]; }
+template <>
+__device__ __forceinline__ void stv<bf16, 1>(bf16* p, const float* v) { *p = __float2bfloat16_rn(v[0]); }
+template <>
+__device__ __forceinline__ void stv<float, 4>(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+template <>
+__device__ __forceinline__ void stv<bf16, 4>(bf16* p, const float* v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+template <typename TO, int PL, int VEC>      // PL = values per lane: C <= 32 * PL; column of value (i, k): (lane + 32 i) VEC + k
 __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                     const float* __restrict__ b, long long rows, int C, float eps, int act,
                                                                     TO* __restrict__ y, float* __restrict__ stats) {
@@ -30,40 +62,52 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_fwd_kernel(const float*
   float v[PL];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < PL; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = c < C ? xr[c] : 0.f;
-    s += v[i];
+  for (int i = 0; i < PL / VEC; ++i) {
+    const int c = (lane + 32 * i) * VEC;
+    if (c < C) ldv<float, VEC>(xr + c, v + i * VEC);
+    else
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[i * VEC + k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) s += v[i * VEC + k];
   }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < PL; ++i) {
-    const int c = lane + 32 * i;
-    const float d = c < C ? v[i] - mean : 0.f;
-    q = fmaf(d, d, q);
+  for (int i = 0; i < PL / VEC; ++i) {
+    const int c = (lane + 32 * i) * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float d = c < C ? v[i * VEC + k] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
 #pragma unroll
-  for (int i = 0; i < PL; ++i) {
-    const int c = lane + 32 * i;
+  for (int i = 0; i < PL / VEC; ++i) {
+    const int c = (lane + 32 * i) * VEC;
     if (c < C) {
-      float o = (v[i] - mean) * rstd * w[c] + b[c];
-      if (act == COR_ACT_GELU) o = gelu_f(o);
-      y[row * C + c] = from_f<TO>(o);
+      float wv[VEC], bv[VEC], o[VEC];
+      ldv<float, VEC>(w + c, wv);
+      ldv<float, VEC>(b + c, bv);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        o[k] = (v[i * VEC + k] - mean) * rstd * wv[k] + bv[k];
+        if (act == COR_ACT_GELU) o[k] = gelu_f(o[k]);
+      }
+      stv<TO, VEC>(y + row * C + c, o);
     }
   }
   if (lane == 0 && stats) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 }
 
 // dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)),  g = dy * act'(.) * w;  dw_part / db_part [gridDim.x][C]
-template <typename TD, int PL>
+template <typename TD, int PL, int VEC>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const TD* __restrict__ dy, const float* __restrict__ x,
                                                                     const float* __restrict__ w, const float* __restrict__ b,
                                                                     const float* __restrict__ stats, long long rows, int C, int act,
                                                                     long long rows_per_cta, float* __restrict__ dx,
                                                                     float* __restrict__ dw_part, float* __restrict__ db_part) {
-  __shared__ float red[kLnWarps][2];
   extern __shared__ float acc_s[];             // [2][kLnWarps][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float aw[PL], ab[PL];
@@ -75,34 +119,50 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_rows_bwd_kernel(const TD* __
     float g[PL], xh[PL];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < PL; ++i) {
-      const int c = lane + 32 * i;
-      g[i] = xh[i] = 0.f;
+    for (int i = 0; i < PL / VEC; ++i) {
+      const int c = (lane + 32 * i) * VEC;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) g[i * VEC + k] = xh[i * VEC + k] = 0.f;
       if (c < C) {
-        xh[i] = (x[row * C + c] - mean) * rstd;
-        float d = to_f<TD>(dy[row * C + c]);
-        if (act == COR_ACT_GELU) d *= gelu_grad(xh[i] * w[c] + b[c]);
-        aw[i] = fmaf(d, xh[i], aw[i]);
-        ab[i] += d;
-        g[i] = d * w[c];
-        s1 += g[i];
-        s2 = fmaf(g[i], xh[i], s2);
+        float xv[VEC], dv[VEC], wv[VEC], bv[VEC];
+        ldv<float, VEC>(x + row * C + c, xv);
+        ldv<TD, VEC>(dy + row * C + c, dv);
+        ldv<float, VEC>(w + c, wv);
+        if (act == COR_ACT_GELU) ldv<float, VEC>(b + c, bv);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const int j = i * VEC + k;
+          xh[j] = (xv[k] - mean) * rstd;
+          float d = dv[k];
+          if (act == COR_ACT_GELU) d *= gelu_grad(xh[j] * wv[k] + bv[k]);
+          aw[j] = fmaf(d, xh[j], aw[j]);
+          ab[j] += d;
+          g[j] = d * wv[k];
+          s1 += g[j];
+          s2 = fmaf(g[j], xh[j], s2);
+        }
       }
     }
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-    for (int i = 0; i < PL; ++i) {
-      const int c = lane + 32 * i;
-      if (c < C) dx[row * C + c] = rstd * (g[i] - s1 - xh[i] * s2);
+    for (int i = 0; i < PL / VEC; ++i) {
+      const int c = (lane + 32 * i) * VEC;
+      if (c < C) {
+        float o[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o[k] = rstd * (g[i * VEC + k] - s1 - xh[i * VEC + k] * s2);
+        stv<float, VEC>(dx + row * C + c, o);
+      }
     }
   }
-  (void)red;
   // fold the 8 warps' column sums in fixed order, publish this CTA's partial
 #pragma unroll
-  for (int i = 0; i < PL; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C) { acc_s[warp * C + c] = aw[i]; acc_s[(kLnWarps + warp) * C + c] = ab[i]; }
+  for (int i = 0; i < PL / VEC; ++i) {
+    const int c = (lane + 32 * i) * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (c + k < C) { acc_s[warp * C + c + k] = aw[i * VEC + k]; acc_s[(kLnWarps + warp) * C + c + k] = ab[i * VEC + k]; }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -143,9 +203,13 @@ extern "C" int cor_ln_rows_fwd(const float* x, const float* weight, const float*
   const unsigned blocks = (unsigned)((rows + kLnWarps - 1) / kLnWarps);
   cudaStream_t st = as_stream(stream);
   COR_REQUIRE(y_dtype == COR_F32 || y_dtype == COR_BF16, "cor_ln_rows_fwd: output dtype %d", y_dtype);
-#define COR_LN_F(TO, PL) ln_rows_fwd_kernel<TO, PL><<<blocks, kLnWarps * 32, 0, st>>>(x, weight, bias, rows, C, eps, act, (TO*)y, stats)
-  if (y_dtype == COR_F32) { if (C <= 256) COR_LN_F(float, 8); else if (C <= 512) COR_LN_F(float, 16); else COR_LN_F(float, 32); }
-  else { if (C <= 256) COR_LN_F(bf16, 8); else if (C <= 512) COR_LN_F(bf16, 16); else COR_LN_F(bf16, 32); }
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(weight) |
+                                   reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+#define COR_LN_F(TO, PL, V) ln_rows_fwd_kernel<TO, PL, V><<<blocks, kLnWarps * 32, 0, st>>>(x, weight, bias, rows, C, eps, act, (TO*)y, stats)
+#define COR_LN_FP(TO, V) do { if (C <= 256) COR_LN_F(TO, 8, V); else if (C <= 512) COR_LN_F(TO, 16, V); else COR_LN_F(TO, 32, V); } while (0)
+  if (y_dtype == COR_F32) { if (vec) COR_LN_FP(float, 4); else COR_LN_FP(float, 1); }
+  else { if (vec) COR_LN_FP(bf16, 4); else COR_LN_FP(bf16, 1); }
+#undef COR_LN_FP
 #undef COR_LN_F
   return check_launch("ln_rows_fwd_kernel");
 }
@@ -161,14 +225,18 @@ extern "C" int cor_ln_rows_bwd(const void* dy, int dy_dtype, const float* x, con
   cudaStream_t st = as_stream(stream);
   const size_t smem = (size_t)2 * kLnWarps * C * sizeof(float);
   COR_REQUIRE(dy_dtype == COR_F32 || dy_dtype == COR_BF16, "cor_ln_rows_bwd: gradient dtype %d", dy_dtype);
-#define COR_LN_B(TD, PL)                                                                                                          \
-  do {                                                                                                                            \
-    COR_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel<TD, PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
-    ln_rows_bwd_kernel<TD, PL><<<parts, kLnWarps * 32, smem, st>>>(reinterpret_cast<const TD*>(dy), x, weight, bias, stats, rows, \
-                                                                   C, act, per, dx, dwp, dbp);                                    \
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(weight) |
+                                   reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+#define COR_LN_B(TD, PL, V)                                                                                                          \
+  do {                                                                                                                               \
+    COR_CUDA(cudaFuncSetAttribute(ln_rows_bwd_kernel<TD, PL, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+    ln_rows_bwd_kernel<TD, PL, V><<<parts, kLnWarps * 32, smem, st>>>(reinterpret_cast<const TD*>(dy), x, weight, bias, stats, rows, \
+                                                                      C, act, per, dx, dwp, dbp);                                    \
   } while (0)
-  if (dy_dtype == COR_F32) { if (C <= 256) COR_LN_B(float, 8); else if (C <= 512) COR_LN_B(float, 16); else COR_LN_B(float, 32); }
-  else { if (C <= 256) COR_LN_B(bf16, 8); else if (C <= 512) COR_LN_B(bf16, 16); else COR_LN_B(bf16, 32); }
+#define COR_LN_BP(TD, V) do { if (C <= 256) COR_LN_B(TD, 8, V); else if (C <= 512) COR_LN_B(TD, 16, V); else COR_LN_B(TD, 32, V); } while (0)
+  if (dy_dtype == COR_F32) { if (vec) COR_LN_BP(float, 4); else COR_LN_BP(float, 1); }
+  else { if (vec) COR_LN_BP(bf16, 4); else COR_LN_BP(bf16, 1); }
+#undef COR_LN_BP
 #undef COR_LN_B
   int rc = check_launch("ln_rows_bwd_kernel");
   if (rc) return rc;

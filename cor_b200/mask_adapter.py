@@ -34,9 +34,66 @@ def masked_pool_tail(clip_feature: torch.Tensor, mask: torch.Tensor) -> torch.Te
     return out.reshape(clip_feature.shape[0], -1).to(torch.promote_types(clip_feature.dtype, mask.dtype))
 
 
+class _AdapterTailFn(torch.autograd.Function):
+    """softmax_P(logsigmoid(maps)) @ feat^T, mean over groups of G maps, as one batched tcgen05 GEMM per direction
+    (csrc/adapter_tail.cu + csrc/gemm_umma.cu).  maps [B,R,h,w] f32, feat [B,C,h,w] -> [B, R/G, C] f32."""
+
+    @staticmethod
+    def forward(ctx, maps, feat, G):
+        from . import _lib as L
+        from .linear import cast_bf16, gemm
+        dev = L.require_cuda(maps, feat)
+        B, R, h, w = maps.shape
+        C, P, Q = feat.shape[1], h * w, R // G
+        Qp = (Q + 63) // 64 * 64
+        m32 = maps.float().contiguous()
+        wq = torch.zeros((B * Qp, P), dtype=torch.bfloat16, device=dev)
+        den = torch.empty((B * R,), dtype=torch.float32, device=dev)
+        ops._call("cor_adapter_tail_weights", dev, ops.ptr(m32), B, R, P, G, Qp, ops.ptr(wq), ops.ptr(den))
+        f16 = cast_bf16(feat.detach().reshape(B * C, P)) if feat.dtype != torch.bfloat16 else feat.detach().reshape(B * C, P).contiguous()
+        out = gemm(wq, f16, Q, C, P, batch=B, a_batch_rows=Qp, b_batch_rows=C)              # [B*Q, C] = Wq[b] feat[b]^T
+        ctx.save_for_backward(m32, den, wq, f16)
+        ctx.cfg = (B, R, P, C, G, Q, Qp, feat.dtype, maps.dtype, tuple(feat.shape), tuple(maps.shape))
+        return out.view(B, Q, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        from .linear import cast_bf16, gemm
+        m32, den, wq, f16 = ctx.saved_tensors
+        B, R, P, C, G, Q, Qp, fdt, mdt, fshape, mshape = ctx.cfg
+        dev = m32.device
+        g16 = torch.zeros((B, Qp, C), dtype=torch.bfloat16, device=dev)                     # zero rows: Qp is the K extent of d feat
+        g16[:, :Q] = g
+        g16 = g16.view(B * Qp, C)
+        gf = gm = None
+        if ctx.needs_input_grad[1]:
+            # d feat[b] (C x P) = g[b]^T (C x Q) Wq[b] (Q x P): both operands stored [K = Qp][rows]
+            gf = gemm(g16, wq, C, P, Qp, a_mn=True, b_mn=True, batch=B, a_batch_rows=Qp, b_batch_rows=Qp).view(fshape).to(fdt)
+        if ctx.needs_input_grad[0]:
+            # d Wq[b] (Q x P) = g[b] (Q x C) feat[b] (C x P): feat stored [K = C][P]
+            gwq = gemm(g16, f16, Q, P, C, b_mn=True, batch=B, a_batch_rows=Qp, b_batch_rows=C)
+            gm = torch.empty((B * R, P), dtype=torch.float32, device=dev)
+            ops._call("cor_adapter_tail_bwd", dev, ops.ptr(m32), ops.ptr(den), ops.ptr(gwq), B, R, P, G, ops.ptr(gm))
+            gm = gm.view(mshape).to(mdt)
+        return gm, gf, None
+
+
+def _tail_gemm_ok(maps: torch.Tensor, feat: torch.Tensor, G: int) -> bool:
+    """Shapes the batched-GEMM tail serves: maps already at the feature resolution, TMA-legal row pitches (P, C multiples
+    of 8) and C a whole number of 64-row K blocks (the MN-major feature operand of d Wq must not run into the next image)."""
+    if not (maps.is_cuda and feat.is_cuda) or maps.dim() != 4 or feat.dim() != 4 or maps.shape[-2:] != feat.shape[-2:]:
+        return False
+    P, C = feat.shape[2] * feat.shape[3], feat.shape[1]
+    return P % 8 == 0 and C % 64 == 0 and maps.shape[1] % G == 0 and G <= 64
+
+
 def softmax_map_pool_tail(maps: torch.Tensor, clip_feature: torch.Tensor, num_output_maps: int) -> torch.Tensor:
     """mask_adapter.py:62-79: softmax_P(logsigmoid(maps)) @ feat^T, mean over groups of maps ->
-    [B, N/num_output_maps, C].  softmax(logsigmoid(x)) == sigmoid(x) / sum sigmoid(x)."""
+    [B, N/num_output_maps, C].  softmax(logsigmoid(x)) == sigmoid(x) / sum sigmoid(x).  Tensor-core path: the mean and the
+    normalisation fold into one bf16 weight row per mask, then one batched GEMM; other shapes take the exact fp32 streaming
+    kernel."""
+    if _tail_gemm_ok(maps, clip_feature, num_output_maps):
+        return _AdapterTailFn.apply(maps, clip_feature, int(num_output_maps))
     return ops.region_pool(clip_feature, maps, transform=ops.W_SIGMOID, normalize=False, group=num_output_maps, eps=0.0,
                            engine="stream").fg
 

@@ -40,19 +40,29 @@ _KERNELS_PER_CALL = {
 TIMING = {"events": None}
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _call(name: str, dev, *args):
+    """One C-ABI call on ``dev``'s current stream.  Host cost matters for the launch-bound small shapes (a few dozen calls
+    per module forward): the device guard is taken only when ``dev`` is not already current and the stream handle comes
+    from the raw accessor (no Stream object)."""
     lib = L.load()
     ev = TIMING["events"]
-    with torch.cuda.device(dev):
-        if ev is not None:
-            st = torch.cuda.current_stream()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(st)
-            rc = getattr(lib, name)(*args, stream_ptr())
-            b.record(st)
-            ev.setdefault(name, []).append((a, b))
-        else:
-            rc = getattr(lib, name)(*args, stream_ptr())
+    idx = dev.index
+    if ev is None and idx is not None and _raw_stream is not None and torch.cuda.current_device() == idx:
+        rc = getattr(lib, name)(*args, L.C.c_void_p(_raw_stream(idx)))
+    else:
+        with torch.cuda.device(dev):
+            if ev is not None:
+                st = torch.cuda.current_stream()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                rc = getattr(lib, name)(*args, stream_ptr())
+                b.record(st)
+                ev.setdefault(name, []).append((a, b))
+            else:
+                rc = getattr(lib, name)(*args, stream_ptr())
     LAUNCHES["count"] += _KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 

@@ -330,6 +330,17 @@ int cor_hyper_logits_fwd(const float* hyper, const void* up, int up_dtype, void*
 int cor_hyper_logits_bwd(const float* hyper, const void* up, int up_dtype, const void* g, int g_dtype, void* d_up,
                          float* d_hyper, int B, int T_all, int t0, int T, int C, long long P, void* work, cor_stream_t stream);
 
+/* Pooling tail of MaskAdapterPooling on the tensor cores (csrc/adapter_tail.cu; lib/support_model/mask_adapter.py:62-79:
+ * softmax over pixels of logsigmoid(maps), mask_weights @ feat^T, mean over the num_output_maps maps of a mask).  The mean
+ * and the per-map normalisation fold into one weight row per mask, Wq[b,q,p] = (1/G) sum_j sigmoid(maps[b,qG+j,p]) / den,
+ * so the pooling is ONE batched cor_gemm_bf16 (out[b] = Wq[b] feat[b]^T).  These two entries are its element-wise ends:
+ *   cor_adapter_tail_weights: maps [B][R][P] f32 -> wq [B][Qp][P] bf16 (rows q >= R/G untouched: the caller zeroes them
+ *                             once so that Qp, a multiple of 64, can serve as a GEMM K extent in the backward), den [B*R].
+ *   cor_adapter_tail_bwd:     gwq [B][R/G][P] f32 (= g_out[b] feat[b], a GEMM) -> gmaps [B][R][P] f32. */
+int cor_adapter_tail_weights(const float* maps, int B, int R, int P, int G, int Qp, void* wq_bf16, float* den, cor_stream_t stream);
+int cor_adapter_tail_bwd(const float* maps, const float* den, const float* gwq, int B, int R, int P, int G, float* gmaps,
+                         cor_stream_t stream);
+
 /* ----------------------------------------------------------------------------------------------
  * (e) Multi-GPU exchange over NVLink peer memory (one process per GPU, one node) - the B200-native replacement of
  * the all-gather of the region rows and the reduce-scatter of their gradient around the similarity stage
