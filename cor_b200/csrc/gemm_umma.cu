@@ -107,29 +107,39 @@ __device__ __forceinline__ uint64_t make_desc_sw128_mnmajor(uint32_t smem_addr) 
 // block so that every global access instruction covers 8 rows x 64 contiguous bytes (16 whole sectors): lane r writes its
 // row (pitch 80 B: the eight lanes of a phase hit eight different 16-byte bank groups), then lane l moves chunk l / 8 of row
 // 8 it + l % 8.  Rows >= rows_valid are skipped (ragged M).  All 32 lanes must call.
-__device__ __forceinline__ void warp_rows_store64(uint8_t* stg, int lane, const uint4 (&c)[4], uint8_t* gbase, long long pitch, int rows_valid) {
+// (explicit shared-space accesses: through a pointer derived from the dynamic-smem base the compiler emitted generic
+// LD / ST, which wait on the long scoreboard)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void warp_rows_store64(uint32_t stg, int lane, const uint4 (&c)[4], uint8_t* gbase, long long pitch, int rows_valid) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(stg + lane * kGmStgPitch + j * 16) = c[j];
+  for (int j = 0; j < 4; ++j) sts128(stg + lane * kGmStgPitch + j * 16, c[j]);
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int r = it * 8 + (lane & 7), ch = lane >> 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(stg + r * kGmStgPitch + ch * 16);
+    const uint4 v = lds128(stg + r * kGmStgPitch + ch * 16);
     if (r < rows_valid) *reinterpret_cast<uint4*>(gbase + r * pitch + ch * 16) = v;
   }
   __syncwarp();
 }
-__device__ __forceinline__ void warp_rows_load64(uint8_t* stg, int lane, uint4 (&c)[4], const uint8_t* gbase, long long pitch, int rows_valid) {
+__device__ __forceinline__ void warp_rows_load64(uint32_t stg, int lane, uint4 (&c)[4], const uint8_t* gbase, long long pitch, int rows_valid) {
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int r = it * 8 + (lane & 7), ch = lane >> 3;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (r < rows_valid) v = *reinterpret_cast<const uint4*>(gbase + r * pitch + ch * 16);
-    *reinterpret_cast<uint4*>(stg + r * kGmStgPitch + ch * 16) = v;
+    sts128(stg + r * kGmStgPitch + ch * 16, v);
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) c[j] = *reinterpret_cast<const uint4*>(stg + lane * kGmStgPitch + j * 16);
+  for (int j = 0; j < 4; ++j) c[j] = lds128(stg + lane * kGmStgPitch + j * 16);
   __syncwarp();
 }
 __device__ __forceinline__ void pack_bf16_16(const float* o, uint4 (&c)[4]) {      // 32 floats -> 64 bytes
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(kGmThreads, 1) gemm_umma_kernel(const __grid_c
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(base + (size_t)kGmStages * 2 * kGmTile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* stg = reinterpret_cast<uint8_t*>(tail) + ((sizeof(GemmSmemTail) + 15) & ~(size_t)15) + (size_t)(warp < kGmEpiWarps ? warp : 0) * kGmStgBytes;
+  const uint32_t stg = smem_u32(reinterpret_cast<uint8_t*>(tail) + ((sizeof(GemmSmemTail) + 15) & ~(size_t)15)) + (uint32_t)((warp < kGmEpiWarps ? warp : 0) * kGmStgBytes);
   const int mt = (g.M + kGmBM - 1) / kGmBM, nt = (g.N + kGmBN - 1) / kGmBN;
   const int ntiles = mt * nt * g.batch;
   const int nkb_all = (g.K + kGmBK - 1) / kGmBK;
