@@ -105,6 +105,9 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_ln_rows_work_bytes", sz, ll, i)
         _sig(lib, "cor_ln_rows_fwd", i, p, p, p, ll, i, f, i, p, i, p, p)
         _sig(lib, "cor_ln_rows_bwd", i, p, i, p, p, p, p, ll, i, i, p, p, p, p, p)
+        _sig(lib, "cor_ln_cf_work_bytes", sz, ll, i, ll)
+        _sig(lib, "cor_ln_cf_fwd", i, p, p, p, ll, i, ll, f, i, p, p)
+        _sig(lib, "cor_ln_cf_bwd", i, p, p, p, p, ll, i, ll, f, i, p, p, p, p, p)
         _sig(lib, "cor_adapter_tail_weights", i, p, i, i, i, i, i, p, p, p)
         _sig(lib, "cor_adapter_tail_bwd", i, p, p, p, i, i, i, i, p, p)
         _sig(lib, "cor_hyper_logits_work_bytes", sz, i, i, i, ll)

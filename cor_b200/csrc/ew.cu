@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(128) act_bwd_vec_kernel(const TD* __restrict__
   float cs[4] = {1.f, 1.f, 1.f, 1.f};
   if (colscale) load4<float>(colscale + n, cs);
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, accs[4] = {0.f, 0.f, 0.f, 0.f};
+  // four rows in flight per thread (A/B on B200: a two-stage software pipeline of 2 + 2 rows measured 5 % slower, 292 vs 278 us
+  // at 147 456 x 1024 -- with ~6 warps per scheduler the other warps already cover a warp's load phase)
   constexpr int U = 4;
   for (long long m = m0; m < m1; m += U) {
     float g[U][4], x[U][4], e[U][4];

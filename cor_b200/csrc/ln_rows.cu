@@ -243,3 +243,153 @@ extern "C" int cor_ln_rows_bwd(const void* dy, int dy_dtype, const float* x, con
   ln_fold_kernel<<<dim3((C + 31) / 32, 2), dim3(32, kFoldTy), 0, st>>>(dwp, dbp, parts, C, dweight, dbias);
   return check_launch("ln_fold_kernel");
 }
+
+// ---- channels-first LayerNorm (+ GELU) over a FEW channels: the two normalisations of mask_downscaling ----------------
+// (lib/support_model/mask_adapter.py:128-142: Conv2d(1,4,3,2) -> LayerNorm2d -> GELU -> Conv2d(4,16,3,2) -> LayerNorm2d ->
+// GELU; LayerNorm(channels_first) :240-251 is mean / pow / sqrt over dim 1, i.e. ~8 element-wise launches forward and ~20
+// backward per norm in eager PyTorch.)  x [N][C][P] fp32, C <= 32: one thread per pixel walks the C channel planes
+// (coalesced across the warp), everything in registers, one launch each way; the affine gradients are per-CTA partial sums
+// folded in fixed order.
+namespace cor {
+
+template <int CMAX>
+__global__ void __launch_bounds__(256) ln_cf_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                       long long N, int C, long long P, float eps, int act, float* __restrict__ y) {
+  const long long total = N * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / P, p = i - n * P;
+    const float* xp = x + n * C * P + p;
+    float v[CMAX];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      v[c] = c < C ? xp[(long long)c * P] : 0.f;
+      s += v[c];
+    }
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      const float d = c < C ? v[c] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(q / (float)C + eps);
+    float* yp = y + n * C * P + p;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        float o = (v[c] - mean) * rstd * w[c] + b[c];
+        if (act == COR_ACT_GELU) o = gelu_f(o);
+        yp[(long long)c * P] = o;
+      }
+    }
+  }
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(256) ln_cf_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ b, long long N, int C, long long P, float eps, int act,
+                                                       float* __restrict__ dx, float* __restrict__ dw_part, float* __restrict__ db_part) {
+  __shared__ float red[8][2 * CMAX];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float aw[CMAX], ab[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) aw[c] = ab[c] = 0.f;
+  const long long total = N * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / P, p = i - n * P;
+    const float* xp = x + n * C * P + p;
+    const float* gp = dy + n * C * P + p;
+    float v[CMAX], g[CMAX];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      v[c] = c < C ? xp[(long long)c * P] : 0.f;
+      g[c] = c < C ? gp[(long long)c * P] : 0.f;
+      s += v[c];
+    }
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      const float d = c < C ? v[c] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(q / (float)C + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < C) {
+        const float xh = (v[c] - mean) * rstd;
+        float d = g[c];
+        if (act == COR_ACT_GELU) d *= gelu_grad(xh * w[c] + b[c]);
+        aw[c] = fmaf(d, xh, aw[c]);
+        ab[c] += d;
+        v[c] = xh;
+        g[c] = d * w[c];
+        s1 += g[c];
+        s2 = fmaf(g[c], xh, s2);
+      }
+    }
+    s1 /= (float)C;
+    s2 /= (float)C;
+    float* op = dx + n * C * P + p;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) op[(long long)c * P] = rstd * (g[c] - s1 - v[c] * s2);
+  }
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    const float a = warp_sum(aw[c]), bb = warp_sum(ab[c]);
+    if (lane == 0) { red[warp][c] = a; red[warp][CMAX + c] = bb; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * CMAX) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    const int c = threadIdx.x < CMAX ? threadIdx.x : threadIdx.x - CMAX;
+    if (c < C) (threadIdx.x < CMAX ? dw_part : db_part)[(long long)blockIdx.x * C + c] = t;
+  }
+}
+
+static int ln_cf_blocks(long long N, long long P) {
+  long long bl = (N * P + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  if (bl > cap) bl = cap;
+  return (int)(bl < 1 ? 1 : bl);
+}
+
+}  // namespace cor
+
+extern "C" size_t cor_ln_cf_work_bytes(long long N, int C, long long P) { return (size_t)ln_cf_blocks(N, P) * C * 2 * sizeof(float) + 16; }
+
+extern "C" int cor_ln_cf_fwd(const float* x, const float* weight, const float* bias, long long N, int C, long long P, float eps, int act,
+                             float* y, cor_stream_t stream) {
+  COR_REQUIRE(x && weight && bias && y, "cor_ln_cf_fwd: null pointer");
+  COR_REQUIRE(N > 0 && P > 0 && C > 0 && C <= 32, "cor_ln_cf_fwd: need 0 < C <= 32 (C=%d)", C);
+  COR_REQUIRE(act == COR_ACT_NONE || act == COR_ACT_GELU, "cor_ln_cf_fwd: act %d", act);
+  const int blocks = ln_cf_blocks(N, P);
+  cudaStream_t st = as_stream(stream);
+  if (C <= 4) ln_cf_fwd_kernel<4><<<blocks, 256, 0, st>>>(x, weight, bias, N, C, P, eps, act, y);
+  else if (C <= 16) ln_cf_fwd_kernel<16><<<blocks, 256, 0, st>>>(x, weight, bias, N, C, P, eps, act, y);
+  else ln_cf_fwd_kernel<32><<<blocks, 256, 0, st>>>(x, weight, bias, N, C, P, eps, act, y);
+  return check_launch("ln_cf_fwd_kernel");
+}
+
+extern "C" int cor_ln_cf_bwd(const float* dy, const float* x, const float* weight, const float* bias, long long N, int C, long long P, float eps,
+                             int act, float* dx, float* dweight, float* dbias, void* work, cor_stream_t stream) {
+  COR_REQUIRE(dy && x && weight && bias && dx && dweight && dbias && work, "cor_ln_cf_bwd: null pointer");
+  COR_REQUIRE(N > 0 && P > 0 && C > 0 && C <= 32, "cor_ln_cf_bwd: need 0 < C <= 32 (C=%d)", C);
+  COR_REQUIRE(act == COR_ACT_NONE || act == COR_ACT_GELU, "cor_ln_cf_bwd: act %d", act);
+  const int blocks = ln_cf_blocks(N, P);
+  float* dwp = reinterpret_cast<float*>(work);
+  float* dbp = dwp + (size_t)blocks * C;
+  cudaStream_t st = as_stream(stream);
+  if (C <= 4) ln_cf_bwd_kernel<4><<<blocks, 256, 0, st>>>(dy, x, weight, bias, N, C, P, eps, act, dx, dwp, dbp);
+  else if (C <= 16) ln_cf_bwd_kernel<16><<<blocks, 256, 0, st>>>(dy, x, weight, bias, N, C, P, eps, act, dx, dwp, dbp);
+  else ln_cf_bwd_kernel<32><<<blocks, 256, 0, st>>>(dy, x, weight, bias, N, C, P, eps, act, dx, dwp, dbp);
+  int rc = check_launch("ln_cf_bwd_kernel");
+  if (rc) return rc;
+  ln_fold_kernel<<<dim3((C + 31) / 32, 2), dim3(32, kFoldTy), 0, st>>>(dwp, dbp, blocks, C, dweight, dbias);
+  return check_launch("ln_fold_kernel");
+}

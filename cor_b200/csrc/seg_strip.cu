@@ -32,7 +32,7 @@ constexpr int kSRing = 32;      // rows of targets kept per column (31-row windo
 constexpr int kSUnroll = kSRing / kSG;   // chunks per unrolled group: one full turn of the ring
 constexpr int kSThreads = kSW + 32;
 constexpr int kSHalo = 15;
-constexpr int kStripFill = 100;   // per cent of the 2 x SM CTA slots a strip height must fill
+constexpr int kStripFill = 85;    // per cent of the 2 x SM CTA slots a strip height must fill (B = 128: 128-row strips = 256 CTAs in one wave 92 us, 64-row strips = 512 CTAs in 1.7 waves 113 us; B = 64: 64-row strips 63 us, 128-row 72 us)
 
 struct StripSmemTail {
   uint64_t full[kSStages], empty[kSStages];

@@ -17,7 +17,7 @@ from . import _lib as L
 from . import ops
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, CorError
 
-__all__ = ["gemm", "linear", "ln_rows", "dwconv7_rows", "cast_bf16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_SIGMOID"]
+__all__ = ["gemm", "linear", "ln_rows", "ln_channels_first", "dwconv7_rows", "cast_bf16", "ACT_NONE", "ACT_RELU", "ACT_GELU", "ACT_SIGMOID"]
 
 _ACTS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "sigmoid": ACT_SIGMOID}
 
@@ -180,6 +180,43 @@ def ln_rows(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: floa
     reference's LayerNorm (mask_adapter.py:226-251) once the tensor is laid out channels-last.  ``out_bf16`` writes the next
     GEMM's A operand directly."""
     return _LnRowsFn.apply(x, weight, bias, float(eps), _ACTS[act], bool(out_bf16))
+
+
+class _LnCfFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, act):
+        dev = L.require_cuda(x, weight, bias)
+        xc = x.float().contiguous()
+        N, Cc = xc.shape[0], xc.shape[1]
+        P = xc[0, 0].numel()
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y = torch.empty_like(xc)
+        ops._call("cor_ln_cf_fwd", dev, ops.ptr(xc), ops.ptr(w), ops.ptr(b), ops._ll(N), Cc, ops._ll(P), ops._f(eps), int(act), ops.ptr(y))
+        ctx.save_for_backward(xc, w, b)
+        ctx.cfg = (float(eps), int(act), weight.dtype, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, w, b = ctx.saved_tensors
+        eps, act, wdt, xdt = ctx.cfg
+        dev = xc.device
+        N, Cc = xc.shape[0], xc.shape[1]
+        P = xc[0, 0].numel()
+        gy = gy.float().contiguous()
+        dx = torch.empty_like(xc)
+        dw = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        db = torch.empty((Cc,), dtype=torch.float32, device=dev)
+        work = ops._work(L.load().cor_ln_cf_work_bytes(N, Cc, P), dev)
+        ops._call("cor_ln_cf_bwd", dev, ops.ptr(gy), ops.ptr(xc), ops.ptr(w), ops.ptr(b), ops._ll(N), Cc, ops._ll(P), ops._f(eps), act,
+                  ops.ptr(dx), ops.ptr(dw), ops.ptr(db), ops.ptr(work))
+        return dx.to(xdt), dw.to(wdt), db.to(wdt), None, None
+
+
+def ln_channels_first(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-6, act: Optional[str] = None) -> torch.Tensor:
+    """LayerNorm over dim 1 of x [N, C, *spatial] (C <= 32) + optional GELU in one launch -- the reference's
+    LayerNorm(data_format="channels_first") (mask_adapter.py:240-251) as used inside mask_downscaling (:128-142)."""
+    return _LnCfFn.apply(x, weight, bias, float(eps), _ACTS[act])
 
 
 class _DwConv7Fn(torch.autograd.Function):

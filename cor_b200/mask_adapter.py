@@ -200,6 +200,15 @@ def _convnext_rows(blk, y: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor
     return linear(hdn, blk.pwconv2.weight, blk.pwconv2.bias, None, None, None, blk.gamma, y)
 
 
+def _md_fusable(md) -> bool:
+    """mask_downscaling as the reference builds it (mask_adapter.py:128-142): conv, LayerNorm2d, GELU, conv, LayerNorm2d, GELU,
+    conv with at most 32 channels inside."""
+    return (len(md) == 7 and isinstance(md[1], LayerNorm) and isinstance(md[4], LayerNorm) and md[1].data_format == "channels_first"
+            and md[4].data_format == "channels_first" and isinstance(md[2], nn.GELU) and isinstance(md[5], nn.GELU)
+            and getattr(md[2], "approximate", "none") == "none" and getattr(md[5], "approximate", "none") == "none"
+            and md[1].weight.numel() <= 32 and md[4].weight.numel() <= 32)
+
+
 def adapter_maps(adapter, clip_feature: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """``get_mask_map(channel_clip_to_maskadapter(clip_feature), mask)`` (mask_adapter.py:59-60) with ``adapter``'s own
     parameters: clip_feature [B,C,h,w], mask [B,Q,h,w] (already at the feature resolution) -> maps [B, Q*num_output_maps, h, w]."""
@@ -211,10 +220,20 @@ def adapter_maps(adapter, clip_feature: torch.Tensor, mask: torch.Tensor) -> tor
     # ChannelReduction (:83-94): 1x1 conv -> LayerNorm(channels_first) -> GELU, on channels-last rows
     x = linear(_rows(clip_feature.float()), cr.conv.weight.view(cr.conv.out_channels, C), cr.conv.bias)
     x = ln_rows(x, cr.norm.weight, cr.norm.bias, cr.norm.eps, "gelu")                                     # [B*P, 512]
-    # mask branch (:157-158): x4 bilinear up, two stride-2 3x3 convs with LN + GELU -> 16 channels at h x w (tiny; cuDNN)
+    # mask branch (:157-158): x4 bilinear up (our resample kernel: the mask carries no gradient), two stride-2 3x3 convs
+    # (cuDNN: a few hundred kFLOP per mask) each followed by LayerNorm2d + GELU in ONE launch of ours (the reference's
+    # channels-first LayerNorm is ~8 element-wise launches forward, ~20 backward) -> 16 channels at h x w
     md = gm.mask_downscaling
-    m = F.interpolate(mask.reshape(B * Q, 1, h, w).float(), size=(4 * h, 4 * w), mode="bilinear", align_corners=False)
-    m16 = md[5](md[4](md[3](md[2](md[1](md[0](m))))))                                                    # [B*Q, 16, h, w]
+    if mask.requires_grad:
+        m = F.interpolate(mask.reshape(B * Q, 1, h, w).float(), size=(4 * h, 4 * w), mode="bilinear", align_corners=False)
+    else:
+        m = ops.mask_prep(mask.reshape(B * Q, h, w).float().contiguous(), (4 * h, 4 * w))[0].view(B * Q, 1, 4 * h, 4 * w)
+    if _md_fusable(md):
+        from .linear import ln_channels_first
+        t = ln_channels_first(md[0](m), md[1].weight, md[1].bias, md[1].eps, "gelu")
+        m16 = ln_channels_first(md[3](t), md[4].weight, md[4].bias, md[4].eps, "gelu")                    # [B*Q, 16, h, w]
+    else:
+        m16 = md[5](md[4](md[3](md[2](md[1](md[0](m))))))
     # fuse(x + conv(m16)) = fuse(x) + (fuse_w conv_w) m16 + fuse_w conv_b + fuse_b   (:161-163; 1x1 convs are linear)
     mid = gm.fuse.out_channels
     fuse_w = gm.fuse.weight.view(mid, -1).float()

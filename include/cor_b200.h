@@ -304,6 +304,16 @@ int cor_ln_rows_fwd(const float* x, const float* weight, const float* bias, long
 int cor_ln_rows_bwd(const void* dy, int dy_dtype /* f32 or bf16 */, const float* x, const float* weight, const float* bias, const float* stats,
                     long long rows, int C, int act, float* dx, float* dweight, float* dbias, void* work, cor_stream_t stream);
 
+/* Channels-first LayerNorm over a few channels (+ GELU), x [N][C][P] f32, C <= 32 (csrc/ln_rows.cu): the two
+ * normalisations of mask_downscaling (lib/support_model/mask_adapter.py:128-142, LayerNorm(channels_first) :240-251 -
+ * mean / pow / sqrt over dim 1 as separate element-wise launches in the reference), one launch forward, one backward
+ * (+ the fold of the affine gradients).  work: cor_ln_cf_work_bytes(N, C, P). */
+size_t cor_ln_cf_work_bytes(long long N, int C, long long P);
+int cor_ln_cf_fwd(const float* x, const float* weight, const float* bias, long long N, int C, long long P, float eps, int act,
+                  float* y, cor_stream_t stream);
+int cor_ln_cf_bwd(const float* dy, const float* x, const float* weight, const float* bias, long long N, int C, long long P, float eps,
+                  int act, float* dx, float* dweight, float* dbias, void* work, cor_stream_t stream);
+
 /* Depth-wise 7x7 convolution (padding 3, stride 1) on channels-last maps [n][h][w][C] f32 (csrc/dwconv.cu): the spatial
  * step of the ConvNeXt blocks (lib/support_model/mask_adapter.py:196-199).  weight [C][49] (nn.Conv2d's [C,1,7,7]), bias [C] or
  * NULL; flip = 1 applies the kernel rotated by 180 degrees = the gradient w.r.t. the input when `in` is d out.

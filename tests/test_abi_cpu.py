@@ -174,6 +174,7 @@ def test_argument_validation_fails_before_any_launch(lib):
         ("cor_gemm_bf16", (one, 0, 8, 0, one, 0, 8, 0, 8, 8, 0, 1, 1.0, null, 0, null, null, null, 0, 8, one, 0, 8, null, 0, null, null)),  # K = 0
         ("cor_gemm_bf16", (one, 0, 8, 0, one, 0, 8, 0, 8, 8, 64, 1, 1.0, null, 9, null, null, null, 0, 8, one, 0, 8, null, 0, null, null)), # unknown activation
         ("cor_hyper_logits_fwd", (one, one, 0, one, 0, 2, 4, 0, 5, 32, 64, null)),       # more tokens than exist
+        ("cor_ln_cf_fwd", (one, one, one, 4, 33, 64, 1e-6, 0, one, null)),               # more channels than the kernel holds
         ("cor_adapter_tail_weights", (one, 2, 12, 64, 8, 64, one, one, null)),           # R not a multiple of the group
         ("cor_adapter_tail_bwd", (one, one, null, 2, 16, 64, 8, one, null)),             # null gradient
         ("cor_infonce_bwd_umma", (one, one, 64, 64, 100, 1.0, one, one, one, 1.0, one, one, one, null)),   # D not a multiple of 64

@@ -151,3 +151,47 @@ def test_pool_tail_on_tensor_cores_vs_streaming_kernel(shape):
     assert rel(got, want) < 4e-3, rel(got, want)                # bf16 weights and features, fp32 accumulation
     assert rel(feat.grad, f2.grad) < 6e-3, rel(feat.grad, f2.grad)
     assert rel(maps.grad, m2.grad) < 1e-2, rel(maps.grad, m2.grad)
+
+
+@pytest.mark.parametrize("shape", [(5, 4, 48, 48), (3, 16, 24, 24), (2, 7, 5, 9), (1, 32, 3, 3)])
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_ln_channels_first_forward_backward_vs_reference_layernorm(shape, act):
+    """cor_ln_cf_fwd / bwd against the module's own channels-first LayerNorm (mean / pow / sqrt over dim 1,
+    mask_adapter.py:240-251) + nn.GELU in fp32 eager."""
+    import torch.nn.functional as F
+    from cor_b200.linear import ln_channels_first
+    from cor_b200.mask_adapter import LayerNorm
+    N, C, H, W = shape
+    g = torch.Generator(device=dev()).manual_seed(N * C + H)
+    x = (1.5 * torch.randn(N, C, H, W, device=dev(), generator=g) + 0.3).requires_grad_(True)
+    ln = LayerNorm(C, eps=1e-6, data_format="channels_first").to(dev())
+    with torch.no_grad():
+        ln.weight.copy_(0.8 + 0.4 * torch.rand(C, device=dev(), generator=g))
+        ln.bias.copy_(0.2 * torch.randn(C, device=dev(), generator=g))
+    y = ln_channels_first(x, ln.weight, ln.bias, ln.eps, act)
+    gy = torch.randn(N, C, H, W, device=dev(), generator=g)
+    y.backward(gy)
+    got = (y.detach(), x.grad.clone(), ln.weight.grad.clone(), ln.bias.grad.clone())
+    x2 = x.detach().clone().requires_grad_(True)
+    ln.weight.grad = ln.bias.grad = None
+    ref = ln(x2)
+    if act == "gelu":
+        ref = F.gelu(ref)
+    ref.backward(gy)
+    torch.testing.assert_close(got[0], ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got[1], x2.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(got[2], ln.weight.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(got[3], ln.bias.grad, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", [(6, 24, 24, 96, 96), (3, 16, 24, 64, 96), (2, 27, 27, 108, 108)])
+def test_mask_resample_kernel_upsamples_like_interpolate(case):
+    """The x4 bilinear up-sampling at the head of mask_downscaling (mask_adapter.py:157) through cor_mask_prep."""
+    import torch.nn.functional as F
+    from cor_b200 import ops
+    n, hm, wm, h, w = case
+    g = torch.Generator(device=dev()).manual_seed(n + hm)
+    m = torch.rand(n, hm, wm, device=dev(), generator=g)
+    got = ops.mask_prep(m, (h, w))[0].view(n, h, w)
+    want = F.interpolate(m[:, None], size=(h, w), mode="bilinear", align_corners=False)[:, 0]
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
