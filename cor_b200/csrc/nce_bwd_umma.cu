@@ -39,6 +39,9 @@ constexpr int kNbYBlk = kNbN * kNbBK * 2;  // 8 KB: one 64-wide k-block of a Y t
 constexpr int kNbMaxSlots = 4;
 constexpr int kNbTmaWarp = 8, kNbMmaWarp = 9;
 constexpr int kNbPrefetch = 3;
+#ifndef COR_NCE_TS
+#define COR_NCE_TS 1                       // 1: the X tile lives in TMEM (GEMM 1 in its A-from-TMEM form); 0: in shared memory (A/B)
+#endif
 
 struct NceSmemTail {
   uint64_t xfull, yfull[kNbMaxSlots], yempty[kNbMaxSlots], s_full[2], s_empty[2], p_full[2], p_empty[2], g_full;
@@ -53,6 +56,7 @@ struct NceArgs {
   const long long* targets;                // [Nq] region index of each query's positive
   const float* g_loss;                     // [1]
   float* out;                              // [gridDim.x][Nx][D] partials (or the result itself when gridDim.x == 1)
+  const bf16* X;                           // [Nx][D] the CTA's rows, read by the epilogue threads when the X tile lives in TMEM
 };
 
 // instruction descriptor with an MN-major B operand (bit 16)
@@ -81,8 +85,8 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
                                                               NceArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
-  uint8_t* x_smem = base;                                                    // nkb x 16 KB
-  uint8_t* y_smem = x_smem + (size_t)a.nkb * kNbBlk;                         // nslots x nkb x 8 KB
+  uint8_t* x_smem = base;                                                    // nkb x 16 KB (only when the X tile is not kept in TMEM)
+  uint8_t* y_smem = x_smem + (COR_NCE_TS ? 0 : (size_t)a.nkb * kNbBlk);      // nslots x nkb x 8 KB
   uint8_t* p_smem = y_smem + (size_t)a.nslots * a.nkb * kNbYBlk;             // 2 buffers x 16 KB
   NceSmemTail* tail = reinterpret_cast<NceSmemTail*>(p_smem + 2 * kNbBlk);
 
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmY);
-    mbar_init(&tail->xfull, 1);
+    mbar_init(&tail->xfull, COR_NCE_TS ? 4 : 1);
     for (int i = 0; i < a.nslots; ++i) { mbar_init(&tail->yfull[i], 1); mbar_init(&tail->yempty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tail->s_full[i], 1); mbar_init(&tail->s_empty[i], 8); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tail->p_full[i], 8); mbar_init(&tail->p_empty[i], 1); }
@@ -108,11 +112,14 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem = tail->tmem_base;
   const uint32_t tmem_g = tmem + 256u;
+  const uint32_t tmem_x = tmem + 128u;             // TS form: X rows in lanes, D/2 packed-bf16 columns [128, 128 + D/2)
 
   if (warp == kNbTmaWarp) {
     if (lane == 0) {
+#if !COR_NCE_TS
       mbar_expect_tx(&tail->xfull, (uint32_t)(a.nkb * kNbBlk));
       for (int kb = 0; kb < a.nkb; ++kb) tma_load_2d(x_smem + kb * kNbBlk, &tmX, &tail->xfull, kb * kNbBK, x0, kEvictNormal);
+#endif
       for (int i = 0; i < n_my && i < kNbPrefetch; ++i)
         for (int kb = 0; kb < a.nkb; ++kb) tma_prefetch_2d(&tmY, kb * kNbBK, ((int)blockIdx.x + i * (int)gridDim.x) * kNbN);
       for (int i = 0; i < n_my; ++i) {
@@ -134,6 +141,7 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
       const uint32_t idesc2 = make_idesc_bf16_bmn(kNbM, D);
       const uint32_t x_base = smem_u32(x_smem), y_base = smem_u32(y_smem), p_base = smem_u32(p_smem);
       mbar_wait(&tail->xfull, 0);
+      tc_fence_after();
       auto gemm1 = [&](int i) {
         const int slot = i % a.nslots, buf = i & 1;
         mbar_wait(&tail->yfull[slot], (i / a.nslots) & 1);
@@ -141,11 +149,20 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
         tc_fence_after();
         if (leader) {
           for (int kb = 0; kb < a.nkb; ++kb) {
-            const uint64_t da = make_desc_sw128(x_base + (uint32_t)(kb * kNbBlk));
             const uint64_t db = make_desc_sw128(y_base + (uint32_t)((slot * a.nkb + kb) * kNbYBlk));
+#if COR_NCE_TS
+            // A from TMEM: 16 k-elements = 8 packed columns per MMA; only the Y tile is fetched from shared memory (with both
+            // operands there the 64 KB X tile was re-read for every 64-row Y tile: 144 KB of operand fetch per tile against
+            // ~1 000 tensor cycles, i.e. shared-memory bandwidth, not the tensor pipe, paced the loop)
+#pragma unroll
+            for (int k = 0; k < kNbBK / 16; ++k)
+              mma_bf16_ts(tmem + (uint32_t)(buf * kNbN), tmem_x + (uint32_t)(kb * (kNbBK / 2) + k * 8), db + 2 * k, idesc1, (kb | k) != 0);
+#else
+            const uint64_t da = make_desc_sw128(x_base + (uint32_t)(kb * kNbBlk));
             mma_bf16_ss(tmem + (uint32_t)(buf * kNbN), da, db, idesc1, kb != 0);
 #pragma unroll
             for (int k = 1; k < kNbBK / 16; ++k) mma_bf16_ss_acc(tmem + (uint32_t)(buf * kNbN), da + 2 * k, db + 2 * k, idesc1);
+#endif
           }
           mma_commit(&tail->s_full[buf]);
         }
@@ -181,6 +198,31 @@ __global__ void __launch_bounds__(320, 1) nce_bwd_umma_kernel(const __grid_const
     const int row = qd * 32 + lane;
     const int xg = x0 + row;
     const bool xok = xg < a.Nx;
+#if COR_NCE_TS
+    // ---- this thread's X row -> TMEM (its own lane), two bf16 per 32-bit column; the four warps of column half 0 cover the
+    // 128 lanes ----
+    if (half == 0) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(a.X + (long long)xg * D);
+      for (int c = 0; c < D / 2; c += 32) {
+        uint32_t v[32];
+        if (xok) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c) + j);
+            v[4 * j] = u.x; v[4 * j + 1] = u.y; v[4 * j + 2] = u.z; v[4 * j + 3] = u.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        tmem_st_32(tmem_x + ((uint32_t)(qd * 32) << 16) + (uint32_t)c, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->xfull);
+    }
+#endif
     const float log2e = 1.4426950408889634f;
     const float gscale = a.g_loss[0] * a.gmul;
     float my_nl = 0.f;                              // mode 0: -lse[q] log2e of this thread's query
@@ -296,7 +338,7 @@ static int nce_launch(const void* X, const void* Y, int Nx, int Ny, int Nq, int 
   rc = encode_tmap_bf16_2d(&tmY, Y, (uint64_t)Ny, (uint64_t)D, kNbN, kNbBK);
   if (rc) return rc;
   // shared memory: X (nkb blocks) + 2 P buffers + as many whole-Y-tile slots as fit (4 at D = 256)
-  const size_t fixed = (size_t)(nkb + 2) * kNbBlk + sizeof(NceSmemTail) + 1024;
+  const size_t fixed = (size_t)((COR_NCE_TS ? 0 : nkb) + 2) * kNbBlk + sizeof(NceSmemTail) + 1024;
   int nslots = (int)((227 * 1024 - fixed) / ((size_t)nkb * kNbYBlk));
   if (nslots > kNbMaxSlots) nslots = kNbMaxSlots;
   COR_REQUIRE(nslots >= 2, "cor_infonce_bwd_umma: shared memory budget (D=%d)", D);
@@ -307,6 +349,7 @@ static int nce_launch(const void* X, const void* Y, int Nx, int Ny, int Nq, int 
   a.c2 = inv_tau * 1.4426950408889634f;
   a.gmul = g_mul * inv_tau / (float)Nq;
   a.lse = lse; a.targets = targets; a.g_loss = g_loss;
+  a.X = reinterpret_cast<const bf16*>(X);
   a.out = nsplit == 1 ? out : part;
   nce_bwd_umma_kernel<<<dim3(nsplit, xtiles), 320, smem, st>>>(tmX, tmY, a);
   rc = check_launch("nce_bwd_umma_kernel");
