@@ -268,10 +268,17 @@ __global__ void __launch_bounds__(256, 1) infonce_bwd_kernel(const bf16* __restr
     for (int q = 0; q < kQT; ++q)
 #pragma unroll
       for (int e = 0; e < 8; ++e) dq[q][e] = 0.f;
-    for (long long r = (long long)blockIdx.x * 8 + warp; r < Nr; r += (long long)gridDim.x * 8) {
+    // the row of the NEXT iteration is loaded before this one is processed: a warp owns ~7 rows at 8 GPUs and the load was a
+    // third of each row's dependent chain
+    const long long rstep = (long long)gridDim.x * 8;
+    long long r = (long long)blockIdx.x * 8 + warp;
+    uint4 raw_next = make_uint4(0u, 0u, 0u, 0u);
+    if (has && r < Nr) raw_next = ld_stream16(reinterpret_cast<const uint4*>(regions + r * D) + lane);
+    for (; r < Nr; r += rstep) {
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const uint4 raw = raw_next;
+      if (has && r + rstep < Nr) raw_next = ld_stream16(reinterpret_cast<const uint4*>(regions + (r + rstep) * D) + lane);
       if (has) {
-        const uint4 raw = ld_stream16(reinterpret_cast<const uint4*>(regions + r * D) + lane);
         f[0] = bf16lo(raw.x); f[1] = bf16hi(raw.x); f[2] = bf16lo(raw.y); f[3] = bf16hi(raw.y);
         f[4] = bf16lo(raw.z); f[5] = bf16hi(raw.z); f[6] = bf16lo(raw.w); f[7] = bf16hi(raw.w);
       }
@@ -366,10 +373,17 @@ __global__ void __launch_bounds__(256, 1) infonce_bwd_regions_kernel(const bf16*
       tgt_s[i] = i < qn ? targets[qc0 + i] : -1;
     }
     __syncthreads();
-    for (long long r = (long long)blockIdx.x * 8 + warp; r < Nr; r += (long long)gridDim.x * 8) {
+    // the row of the NEXT iteration is loaded before this one is processed: a warp owns ~7 rows at 8 GPUs and the load was a
+    // third of each row's dependent chain
+    const long long rstep = (long long)gridDim.x * 8;
+    long long r = (long long)blockIdx.x * 8 + warp;
+    uint4 raw_next = make_uint4(0u, 0u, 0u, 0u);
+    if (has && r < Nr) raw_next = ld_stream16(reinterpret_cast<const uint4*>(regions + r * D) + lane);
+    for (; r < Nr; r += rstep) {
       float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const uint4 raw = raw_next;
+      if (has && r + rstep < Nr) raw_next = ld_stream16(reinterpret_cast<const uint4*>(regions + (r + rstep) * D) + lane);
       if (has) {
-        const uint4 raw = ld_stream16(reinterpret_cast<const uint4*>(regions + r * D) + lane);
         f[0] = bf16lo(raw.x); f[1] = bf16hi(raw.x); f[2] = bf16lo(raw.y); f[3] = bf16hi(raw.y);
         f[4] = bf16lo(raw.z); f[5] = bf16hi(raw.z); f[6] = bf16lo(raw.w); f[7] = bf16hi(raw.w);
       }
