@@ -130,6 +130,8 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_peer_wait_exit", i, p, p, i, i, i, p)
         _sig(lib, "cor_peer_gather_rows", i, p, p, ll, p, p, i, i, i, p)
         _sig(lib, "cor_peer_reduce_rows", i, p, p, ll, p, p, i, i, i, p)
+        _sig(lib, "cor_peer_gather_sim_work_bytes", sz)
+        _sig(lib, "cor_peer_gather_sim", i, p, p, ll, i, p, i, f, p, p, p, p, i, i, i, p)
         if lib.cor_abi_version() != ABI_VERSION:
             raise CorError(f"ABI version mismatch: library {lib.cor_abi_version()}, binding {ABI_VERSION}; rebuild with `python -m cor_b200.build`")
         _lib = lib

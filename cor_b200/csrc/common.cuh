@@ -83,6 +83,29 @@ __device__ __forceinline__ float warp_min(float v) {
   return v;
 }
 
+constexpr int kQT = 16;          // queries per tile of the streaming similarity kernels (one lane per query after the transposed reduce)
+
+// ---- warp-per-region-row similarity: transposed butterfly -------------------------------------------
+// After the per-lane partial dot products a transposed butterfly leaves S[q0+lane, r] in lane `lane`
+// (lanes >= kQT idle): 16+8+4+2+1 = 31 shuffles instead of 16*5.
+__device__ __forceinline__ float transpose_reduce16(float (&a)[kQT], int lane) {
+  // step 1: fold the two half-warps; every lane keeps all 16 partials
+#pragma unroll
+  for (int q = 0; q < kQT; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], 16);
+  // steps 2..5: keep the half that belongs to this lane's bit
+#pragma unroll
+  for (int s = 8, n = kQT; s >= 1; s >>= 1, n >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int q = 0; q < n / 2; ++q) {
+      const float mine = up ? a[q + n / 2] : a[q];
+      const float theirs = up ? a[q] : a[q + n / 2];
+      a[q] = mine + __shfl_xor_sync(0xffffffffu, theirs, s);
+    }
+  }
+  return a[0];   // lane l (l < 16, counting bits 8,4,2,1) holds query index l
+}
+
 // ---- GELU (erf form, torch nn.GELU() default) on the SFU, branch-free --------------------------------------------------
 // 1 - Phi(|x|) = 0.5 erfc(|x| / sqrt 2) through Abramowitz-Stegun 7.1.26: erfc(z) = (a1 t + .. + a5 t^5) exp(-z^2),
 // t = 1 / (1 + p z), |error| <= 1.5e-7 absolute.  MUFU.RCP + MUFU.EX2 + 9 FMA-pipe instructions; the 0.5 is folded into

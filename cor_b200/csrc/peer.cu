@@ -151,6 +151,90 @@ __global__ void __launch_bounds__(kPeerThreads) peer_gather_kernel(const uint4* 
   peer_exit(c, epoch);
 }
 
+// ---- fused all-gather + similarity (few local queries) ----------------------------------------------------------------
+// The forward exchange and its consumer in ONE kernel: every region row is pulled over NVLink exactly once, written into
+// the local gathered buffer (the backward and the target-logit gather read it there) and, while it is in registers, dotted
+// with this rank's <= 16 queries -- the online log-sum-exp partials of the InfoNCE forward.  Replaces peer_gather_kernel +
+// the similarity kernel of the step (two launches, two passes over the gathered rows, one of them through HBM).
+// Warp per row, one 16-byte vector per lane (D <= 256), two rows prefetched ahead of the row being processed so the
+// ~2 us NVLink latency overlaps the arithmetic; rows are walked ring-wise starting with the rank's own slice.
+// part layout = the streaming similarity kernel's: [gridDim.x][kQT][2] (running max, sum) for cor_infonce_tail.
+constexpr int kPgsThreads = 256;
+__global__ void __launch_bounds__(kPgsThreads) peer_gather_sim_kernel(const uint4* const* __restrict__ src, uint4* __restrict__ all,
+                                                                      long long n_local, int D, const bf16* __restrict__ queries, int Nq,
+                                                                      float inv_tau, float* __restrict__ part, PeerCtl c) {
+  extern __shared__ float qs[];   // [kQT][D]
+  __shared__ float cm[kPgsThreads / 32][kQT], cs[kPgsThreads / 32][kQT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kQT * D; i += blockDim.x) {
+    const int q = i / D, d = i - q * D;
+    qs[i] = q < Nq ? __bfloat162float(queries[(long long)q * D + d]) : 0.f;
+  }
+  const unsigned epoch = peer_enter(c);          // includes a __syncthreads: qs is complete, every peer's rows are published
+  const int nvec = D / 8;
+  const bool has = lane < nvec;
+  const long long total = n_local * c.world, step = (long long)gridDim.x * (kPgsThreads / 32);
+  auto fetch = [&](long long g, uint4& v, long long& dst) {
+    const int k = (int)(g / n_local);
+    const int p = (c.rank + k) % c.world;
+    const long long i = g - (long long)k * n_local;
+    dst = ((long long)p * n_local + i) * nvec + lane;
+    v = ld_peer16(src[p] + i * nvec + lane);
+  };
+  float m = -INFINITY, s = 0.f;
+  long long g = (long long)blockIdx.x * (kPgsThreads / 32) + warp;
+  uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+  long long d0 = 0, d1 = 0;
+  if (has && g < total) fetch(g, v0, d0);
+  if (has && g + step < total) fetch(g + step, v1, d1);
+  for (; g < total; g += step) {
+    const uint4 raw = v0;
+    const long long dst = d0;
+    v0 = v1;
+    d0 = d1;
+    if (has && g + 2 * step < total) fetch(g + 2 * step, v1, d1);
+    float a[kQT];
+#pragma unroll
+    for (int q = 0; q < kQT; ++q) a[q] = 0.f;
+    if (has) {
+      all[dst] = raw;
+      float f[8];
+      f[0] = bf16lo(raw.x); f[1] = bf16hi(raw.x); f[2] = bf16lo(raw.y); f[3] = bf16hi(raw.y);
+      f[4] = bf16lo(raw.z); f[5] = bf16hi(raw.z); f[6] = bf16lo(raw.w); f[7] = bf16hi(raw.w);
+#pragma unroll
+      for (int q = 0; q < kQT; ++q) {
+        const float4 x = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8]);
+        const float4 y = *reinterpret_cast<const float4*>(&qs[q * D + lane * 8 + 4]);
+        a[q] = fmaf(f[0], x.x, a[q]); a[q] = fmaf(f[1], x.y, a[q]); a[q] = fmaf(f[2], x.z, a[q]); a[q] = fmaf(f[3], x.w, a[q]);
+        a[q] = fmaf(f[4], y.x, a[q]); a[q] = fmaf(f[5], y.y, a[q]); a[q] = fmaf(f[6], y.z, a[q]); a[q] = fmaf(f[7], y.w, a[q]);
+      }
+    }
+    const float sv = transpose_reduce16(a, lane);
+    if (lane < kQT && lane < Nq) {
+      const float x = sv * inv_tau;
+      if (x > m) { s = s * __expf(m - x) + 1.f; m = x; } else { s += __expf(x - m); }
+    }
+  }
+  if (lane < kQT) { cm[warp][lane] = m; cs[warp][lane] = s; }
+  __syncthreads();
+  if (threadIdx.x < kQT) {
+    float M = -INFINITY;
+    for (int w = 0; w < kPgsThreads / 32; ++w) M = fmaxf(M, cm[w][threadIdx.x]);
+    float Ssum = 0.f;
+    for (int w = 0; w < kPgsThreads / 32; ++w) Ssum += (cm[w][threadIdx.x] == -INFINITY) ? 0.f : cs[w][threadIdx.x] * __expf(cm[w][threadIdx.x] - M);
+    float* o = part + ((long long)blockIdx.x * kQT + threadIdx.x) * 2;
+    o[0] = M; o[1] = Ssum;
+  }
+  peer_exit(c, epoch);
+}
+
+static int peer_gather_sim_grid(long long rows) {
+  long long g = (rows + 2 * (kPgsThreads / 32) - 1) / (2 * (kPgsThreads / 32));      // >= 2 rows per warp
+  const long long cap = sm_count();
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
 // out[i] = sum over ranks p (ascending) of src[p][rank*vecs + i]; float4 vectors.
 template <int W>
 __device__ __forceinline__ void reduce_body(const uint4* const* __restrict__ src, float4* __restrict__ out, long long vecs, int rank,
@@ -297,6 +381,28 @@ int cor_peer_gather_rows(const void* const* peer_src, void* all, long long bytes
   peer_gather_kernel<<<peer_grid(vecs * world), kPeerThreads, 0, as_stream(stream)>>>(reinterpret_cast<const uint4* const*>(peer_src),
                                                                                      reinterpret_cast<uint4*>(all), vecs, c);
   return check_launch("peer_gather_kernel");
+}
+
+size_t cor_peer_gather_sim_work_bytes(void) { return (size_t)sm_count() * kQT * 2 * sizeof(float) + 16; }
+
+int cor_peer_gather_sim(const void* const* peer_src, void* all, long long n_local, int D, const void* queries, int Nq, float inv_tau,
+                        float* part, int* nparts, void* const* peer_flags, void* state, int rank, int world, int channel,
+                        cor_stream_t stream) {
+  COR_REQUIRE(peer_src && all && queries && part && nparts && peer_flags && state, "cor_peer_gather_sim: null pointer");
+  COR_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "cor_peer_gather_sim: rank %d / world %d (max %d)", rank,
+              world, kPeerMaxWorld);
+  COR_REQUIRE(channel == 0 || channel == 1, "cor_peer_gather_sim: channel %d", channel);
+  COR_REQUIRE(n_local > 0 && D > 0 && D % 8 == 0 && D <= 256, "cor_peer_gather_sim: need D %% 8 == 0 and D <= 256 (D=%d)", D);
+  COR_REQUIRE(Nq > 0 && Nq <= kQT, "cor_peer_gather_sim: at most %d local queries (Nq=%d)", kQT, Nq);
+  COR_REQUIRE((uintptr_t)all % 16 == 0, "cor_peer_gather_sim: gathered buffer must be 16-byte aligned");
+  PeerCtl c{reinterpret_cast<unsigned* const*>(peer_flags), reinterpret_cast<unsigned*>(state), rank, world, channel, peer_timeout_ns()};
+  const int grid = peer_gather_sim_grid(n_local * world);
+  const size_t smem = (size_t)kQT * D * sizeof(float);
+  peer_gather_sim_kernel<<<grid, kPgsThreads, smem, as_stream(stream)>>>(reinterpret_cast<const uint4* const*>(peer_src),
+                                                                        reinterpret_cast<uint4*>(all), n_local, D,
+                                                                        reinterpret_cast<const bf16*>(queries), Nq, inv_tau, part, c);
+  *nparts = grid;
+  return check_launch("peer_gather_sim_kernel");
 }
 
 int cor_peer_reduce_rows(const void* const* peer_src, float* out, long long floats_per_rank, void* const* peer_flags, void* state,

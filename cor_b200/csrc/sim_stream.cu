@@ -9,8 +9,6 @@
 
 namespace cor {
 
-constexpr int kQT = 16;          // queries per tile (one lane per query after the transposed reduce)
-
 // ---- row L2 normalise ------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) l2_normalize_kernel(const T* __restrict__ x, int D, float* __restrict__ y32,
@@ -32,27 +30,7 @@ __global__ void __launch_bounds__(128) l2_normalize_kernel(const T* __restrict__
   if (threadIdx.x == 0 && inv_norm) inv_norm[row] = inv;
 }
 
-// ---- S = Q R^T, warp per region row ---------------------------------------------------------------
-// After the per-lane partial dot products a transposed butterfly leaves S[q0+lane, r] in lane `lane`
-// (lanes >= kQT idle): 16+8+4+2+1 = 31 shuffles instead of 16*5.
-__device__ __forceinline__ float transpose_reduce16(float (&a)[kQT], int lane) {
-  // step 1: fold the two half-warps; every lane keeps all 16 partials
-#pragma unroll
-  for (int q = 0; q < kQT; ++q) a[q] += __shfl_xor_sync(0xffffffffu, a[q], 16);
-  // steps 2..5: keep the half that belongs to this lane's bit
-#pragma unroll
-  for (int s = 8, n = kQT; s >= 1; s >>= 1, n >>= 1) {
-    const bool up = lane & s;
-#pragma unroll
-    for (int q = 0; q < n / 2; ++q) {
-      const float mine = up ? a[q + n / 2] : a[q];
-      const float theirs = up ? a[q] : a[q + n / 2];
-      a[q] = mine + __shfl_xor_sync(0xffffffffu, theirs, s);
-    }
-  }
-  return a[0];   // lane l (l < 16, counting bits 8,4,2,1) holds query index l
-}
-
+// ---- S = Q R^T, warp per region row (transpose_reduce16: common.cuh) -----------------------------------
 // grid = (region CTAs, query tiles); block = 256.  dynamic smem = kQT * D floats.
 // work layout: part [qtiles][gridDim.x][kQT][2] (running max, sum) -> lse by sim_lse_combine_kernel.
 __global__ void __launch_bounds__(256) sim_stream_kernel(const bf16* __restrict__ regions, const bf16* __restrict__ queries, int Nr,

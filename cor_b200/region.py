@@ -99,6 +99,20 @@ def _overlap_enabled():
     return os.environ.get("COR_STEP_OVERLAP", "1") != "0"
 
 
+def _peer_fused_ok(n_queries: int, C: int, n_regions: int = 0, sim_engine: str = "auto") -> bool:
+    """Shapes the fused gather + similarity kernel serves (a rank's <= 16 queries, one 16-byte vector per lane) and for which
+    it wins: whenever the separate path would score on the streaming kernel.  Once the gathered gallery is large enough for
+    the tensor-core similarity kernel (8 GPUs x 1024 regions) the pull kernel + that kernel measure 3 us faster per step
+    (0.848 vs 0.851 ms at 8 GPUs; at 2 GPUs the fused kernel wins 0.8136 vs 0.8161 ms).  ``COR_PEER_FUSED=0`` / ``=2``
+    force the separate / the fused kernels (A/B)."""
+    knob = os.environ.get("COR_PEER_FUSED", "1")
+    if knob == "0" or n_queries > 16 or C % 8 or C > 256:
+        return False
+    if knob == "2":
+        return True
+    return ops._sim_engine(n_queries, n_regions, C, sim_engine) != "umma"
+
+
 class _FusedStepFn(torch.autograd.Function):
     """The whole region path as ONE autograd node: every kernel of the forward is launched back to
     back on the current stream, the backward is written out by hand, and no tensor glue (slices,
@@ -203,9 +217,14 @@ class _FusedStepFn(torch.autograd.Function):
         # A/B on one 8xB200 box (profiles/README.md): reduce-scatter of the region gradient 0.951 ms/step, collective-free
         # variant 0.965 ms/step -> the reduce-scatter stays the default; COR_STEP_BWD=local selects the other.
         local_bwd = os.environ.get("COR_STEP_BWD", "reduce_scatter") == "local"
+        fused_parts = None
         if gather and ws > 1:
             r16 = torch.empty((ws * n_local, Cc), dtype=torch.bfloat16, device=dev)
-            if px is not None:
+            if px is not None and not local_bwd and _peer_fused_ok(B, Cc, ws * n_local, sim_engine):
+                # ONE kernel: pull the peers' rows over NVLink, keep a local copy for the backward, and score every row
+                # against this rank's queries while it is in registers (all-gather fused with its consumer)
+                fused_parts = px.gather_sim(r16, q16, inv_tau)
+            elif px is not None:
                 px.gather(r16)               # our own pull-over-NVLink kernel: no NCCL on the data path
             else:
                 torch.distributed.all_gather_into_tensor(r16, fg16)
@@ -234,7 +253,7 @@ class _FusedStepFn(torch.autograd.Function):
         if lse is None:
             # similarity with its log-sum-exp partials left in the work buffer, then ONE tail kernel: partial merge ->
             # lse, target logits, InfoNCE mean and the step's total loss
-            sim_work, nparts, qt = ops._sim_lse_parts(r16, q16, inv_tau, sim_engine)
+            sim_work, nparts, qt = fused_parts if fused_parts is not None else ops._sim_lse_parts(r16, q16, inv_tau, sim_engine)
             lse = torch.empty((B,), **f32)
             if side is not None:
                 cur.wait_stream(side)        # join: the total needs the segmentation and fg/bg losses

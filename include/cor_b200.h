@@ -388,6 +388,16 @@ int cor_peer_gather_rows(const void* const* peer_src, void* all, long long bytes
                          int rank, int world, int channel, cor_stream_t stream);
 int cor_peer_reduce_rows(const void* const* peer_src, float* out, long long floats_per_rank, void* const* peer_flags, void* state,
                          int rank, int world, int channel, cor_stream_t stream);
+/* Fused all-gather + similarity for a rank's few (<= 16) queries: ONE kernel pulls every peer's region rows over NVLink
+ * once, writes them into the local gathered buffer `all` [world*n_local][D] bf16 (rank-major, what cor_peer_gather_rows
+ * produces) and, while a row is in registers, scores it against `queries` [Nq][D] bf16 -- leaving the log-sum-exp partials
+ * `part` [*nparts][16][2] in the layout cor_infonce_tail consumes (same as cor_sim_lse_parts, qt = 16).  Same flag protocol
+ * as cor_peer_gather_rows (enter barrier on `channel`, exit flag).  D % 8 == 0, D <= 256.
+ * part: cor_peer_gather_sim_work_bytes() bytes. */
+size_t cor_peer_gather_sim_work_bytes(void);
+int cor_peer_gather_sim(const void* const* peer_src, void* all, long long n_local, int D, const void* queries, int Nq, float inv_tau,
+                        float* part, int* nparts, void* const* peer_flags, void* state, int rank, int world, int channel,
+                        cor_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,7 @@ def main():
         out.loss.backward()
         return out.loss.detach().clone(), pred.grad.clone(), emb.grad.float().clone(), comb.grad.clone()
 
+    os.environ["COR_PEER_FUSED"] = "0"           # separate gather and similarity kernels: the arithmetic of the NCCL path
     a = run(True)
     assert any(k[0] == 4 * 16 and k[1] == 128 and px_.ok for k, px_ in peer._CACHE.items()), "the fused step did not use the peer exchange"
     b = run(False)
@@ -76,6 +77,14 @@ def main():
             assert torch.equal(x, y), f"{nm}: peer vs nccl differ by {(x - y).abs().max().item()}"
         else:                                    # NCCL's reduction order is its own for ws > 2
             torch.testing.assert_close(x, y, rtol=2e-2 if nm == "g_emb" else 1e-4, atol=1e-5, msg=nm)
+    # the fused gather + similarity kernel (default): same rows, log-sum-exp partials merged in another order
+    os.environ["COR_PEER_FUSED"] = "2"           # forced: at 8 GPUs the default would pick the separate kernels
+    assert region._peer_fused_ok(4, 128, ws * 64)
+    f = run(True)
+    for x, y, nm in zip(f, a, names):
+        assert torch.isfinite(x).all(), nm
+        torch.testing.assert_close(x, y, rtol=2e-2 if nm == "g_emb" else 1e-4, atol=1e-5, msg="fused gather+sim: " + nm)
+    os.environ["COR_PEER_FUSED"] = "1"
     # ---- graph replay: epochs advance on the device; replays reproduce the eager step bit for bit ----
     os.environ["COR_PEER"] = "1"
     bufs = region.StepBuffers(4, 16, C=128, h=16, w=16, H=128, W=128, hp=32, wp=32, device=dev, emb_dtype=torch.bfloat16)

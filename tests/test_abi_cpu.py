@@ -165,6 +165,7 @@ def test_argument_validation_fails_before_any_launch(lib):
         ("cor_peer_gather_rows", (one, one, 1000, one, one, 0, 2, 0, null)),             # bytes not a multiple of 16
         ("cor_peer_gather_rows", (one, one, 1024, one, one, 3, 2, 0, null)),             # rank outside the world
         ("cor_peer_reduce_rows", (one, one, 1024, one, one, 0, 64, 1, null)),            # world beyond cor_peer_max_world()
+        ("cor_peer_gather_sim", (one, one, 64, 256, one, 17, 14.0, one, one, one, one, 0, 2, 0, null)),   # more queries than a tile
         ("cor_peer_signal", (one, one, 0, 2, 5, null)),                                  # channel out of range
         ("cor_infonce_tail", (null, 4, 16, one, one, one, 8, 4, 64, 1.0, one, one, one, null, null, 0.0, 0.0, 0.0, null, null)),
         ("cor_infonce_tail", (one, 4, 16, one, one, one, 8, 4, 64, 1.0, one, one, one, null, null, 0.0, 0.0, 0.0, one, null)),  # total without seg/fgbg

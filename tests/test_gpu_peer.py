@@ -59,6 +59,23 @@ class _VirtualRank:
                   ops.ptr(self.flag_ptrs), ops.ptr(self.state), self.rank, self.world, 0)
         return out
 
+    def gather_sim(self, q16, inv_tau):
+        """Fused all-gather + similarity: (gathered rows, lse of this rank's queries merged from the kernel's partials)."""
+        import ctypes as C_
+        from cor_b200 import _lib as L, ops
+        lib = L.load()
+        out = torch.empty((self.world * self.n, self.C), dtype=torch.bfloat16, device=self.pub.device)
+        work = torch.zeros(lib.cor_peer_gather_sim_work_bytes() // 4, dtype=torch.float32, device=out.device)
+        nparts = C_.c_int(0)
+        ops._call("cor_peer_gather_sim", out.device, ops.ptr(self.pub_ptrs), ops.ptr(out), ops._ll(self.n), self.C, ops.ptr(q16),
+                  int(q16.shape[0]), ops._f(inv_tau), ops.ptr(work), C_.byref(nparts), ops.ptr(self.flag_ptrs), ops.ptr(self.state),
+                  self.rank, self.world, 0)
+        parts = work[:nparts.value * 16 * 2].view(nparts.value, 16, 2).double()
+        m, sm = parts[..., 0], parts[..., 1]
+        M = m.max(dim=0).values
+        lse = M + torch.log((sm * torch.exp(m - M)).nan_to_num(0.0).sum(dim=0))
+        return out, lse[:q16.shape[0]]
+
     def reduce(self):
         from cor_b200 import ops
         out = torch.empty((self.n, self.C), dtype=torch.float32, device=self.pub.device)
@@ -94,7 +111,17 @@ def test_peer_kernels_lock_step_on_one_gpu(world):
             r.ctl("cor_peer_signal", 0)
         want = torch.cat(rows)
         for r in ranks:
-            assert torch.equal(r.gather(), want), f"gather mismatch, rank {r.rank}, epoch {it}"
+            if it % 2 == 0:
+                assert torch.equal(r.gather(), want), f"gather mismatch, rank {r.rank}, epoch {it}"
+            else:
+                # the fused gather + similarity kernel: same protocol, same gathered rows, plus the log-sum-exp of the rank's
+                # own queries against every row
+                nq = 16 if r.rank % 2 == 0 else 5
+                q16 = torch.nn.functional.normalize(torch.randn(nq, Cc, device=dev, generator=g), dim=-1).bfloat16()
+                got, lse = r.gather_sim(q16, 1.0 / 0.07)
+                assert torch.equal(got, want), f"fused gather mismatch, rank {r.rank}, epoch {it}"
+                ref = torch.logsumexp((q16.double() @ want.double().t()) / 0.07, dim=-1)
+                torch.testing.assert_close(lse, ref, rtol=1e-5, atol=2e-3)
         if it >= 2:
             continue
         grads = [torch.randn(world * n, Cc, device=dev, generator=g) for _ in range(world)]
