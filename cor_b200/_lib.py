@@ -97,6 +97,7 @@ def load(path: str = LIB_PATH):
         _sig(lib, "cor_gemm_bf16_work_bytes", sz, i, i, i, i, i)
         _sig(lib, "cor_gemm_bf16", i, p, i, ll, ll, p, i, ll, ll, i, i, i, i, f, p, i, p, p, p, i, ll, p, i, ll, p, i, p, p)
         _sig(lib, "cor_cast_cat_bf16", i, p, i, p, i, ll, p, p)
+        _sig(lib, "cor_cast_pad_rows_bf16", i, p, i, i, i, i, p, p)
         _sig(lib, "cor_act_bwd_work_bytes", sz, ll, i)
         _sig(lib, "cor_act_bwd", i, p, i, p, p, p, p, i, ll, i, p, p, p, p, p)
         _sig(lib, "cor_dwconv7_work_bytes", sz, i, i, i, i)

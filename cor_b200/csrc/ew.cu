@@ -33,6 +33,25 @@ __global__ void __launch_bounds__(256) cast_cat_bf16_vec_kernel(const float* __r
   }
 }
 
+// out[b][r][:] = bf16(src[b][r][:]) for r < rows, 0 for rows <= r < rows_padded: a K-padded MN-major GEMM operand (the zero rows
+// make whatever the other operand holds at those k indices irrelevant).  4 columns per thread.
+__global__ void __launch_bounds__(256) cast_pad_rows_bf16_kernel(const float* __restrict__ src, int rows, int rows_padded, int cols4,
+                                                                long long total, bf16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / cols4;
+    const int c = (int)(i - row * cols4);
+    const long long b = row / rows_padded;
+    const int r = (int)(row - b * rows_padded);
+    uint2 o = make_uint2(0u, 0u);
+    if (r < rows) {
+      const float4 v = reinterpret_cast<const float4*>(src)[(b * rows + r) * cols4 + c];
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      o = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+}
+
 // dz[m][n] = dy[m][n] * emul[m][n] * colscale[n] * act'(.)  (bf16, the A operand of dX = dZ W and dW = dZ^T X);
 // db[n] = sum_m dz (f32); dcs[n] = sum_m dy[m][n] * emul * act(pre)[m][n] (gradient of the column scale, ConvNeXt's gamma).
 // y = the activation's OUTPUT before mask / scale (relu, sigmoid) or pre = its pre-activation (gelu; also the un-scaled
@@ -173,6 +192,17 @@ extern "C" int cor_cast_cat_bf16(const float* a, int c0, const float* b, int c1,
   }
   cast_cat_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, c0, b, c1, rows, reinterpret_cast<bf16*>(out_bf16));
   return check_launch("cast_cat_bf16_kernel");
+}
+
+extern "C" int cor_cast_pad_rows_bf16(const float* src, int batch, int rows, int rows_padded, int cols, void* out_bf16, cor_stream_t stream) {
+  COR_REQUIRE(src && out_bf16, "cor_cast_pad_rows_bf16: null pointer");
+  COR_REQUIRE(batch > 0 && rows > 0 && rows_padded >= rows && cols > 0 && cols % 4 == 0, "cor_cast_pad_rows_bf16: bad shape (rows=%d padded=%d cols=%d)",
+              rows, rows_padded, cols);
+  COR_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out_bf16)) & 15) == 0, "cor_cast_pad_rows_bf16: 16-byte alignment required");
+  const long long total = (long long)batch * rows_padded * (cols / 4);
+  const int blocks = (int)((total + 255) / 256 < (long long)sm_count() * 8 ? (total + 255) / 256 : (long long)sm_count() * 8);
+  cast_pad_rows_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, rows, rows_padded, cols / 4, total, reinterpret_cast<bf16*>(out_bf16));
+  return check_launch("cast_pad_rows_bf16_kernel");
 }
 
 extern "C" size_t cor_act_bwd_work_bytes(long long M, int N) { return (size_t)act_chunks(M, N) * N * 2 * sizeof(float) + 16; }

@@ -136,7 +136,8 @@ def _umma_weight_buffer(dev, B, Rp, R, P, ones_row=True):
         if ones_row:
             buf[:, R, :] = 1.0
         _umma_w_cache[key] = buf
-    return buf
+    buf._cor_epoch = getattr(buf, "_cor_epoch", 0) + 1       # every hand-out precedes a rewrite by mask_prep: a backward that
+    return buf                                                # wants these weights checks that no later forward replaced them
 
 
 def clear_caches():

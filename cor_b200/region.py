@@ -269,6 +269,7 @@ class _FusedStepFn(torch.autograd.Function):
         ctx.cfg = (B, M, Cc, h, w, float(inv_tau), float(nce_weight), int(bg_mode), float(w_fg), float(w_bg), ws, offset, n_local,
                    pred.dtype, emb.dtype, comb.dtype, tuple(comb.shape), need_pred, need_emb, comb.requires_grad)
         ctx.px = px
+        ctx.w16 = (w16, getattr(w16, "_cor_epoch", -1))      # not a saved tensor: a cached operand buffer, validated by its epoch
         ctx.mark_non_differentiable(fg, out8, out4, nce)
         ctx.set_materialize_grads(False)     # no zero-filled gradients for the auxiliary outputs
         return loss[0], out8, out4, nce, fg
@@ -364,8 +365,24 @@ class _FusedStepFn(torch.autograd.Function):
                 gs_bg_full = torch.zeros((B, M, Cc), **f32)
                 gs_bg_full[:, 0, :] = gs_bg
             g_emb_c = torch.empty((B, Cc, h, w), dtype=emb_dt if emb_dt in (torch.float32, torch.bfloat16) else torch.float32, device=dev)
-            name = "cor_pool_bwd_umma" if lib.cor_pool_bwd_umma_ok(B, Cc, P, M, int(gs_bg_full is not None)) else "cor_pool_bwd_feat"
-            call(name, dev, ptr(gs_fg), ptr(gs_bg_full), ptr(w32), _ll(P), B, Cc, P, M, ops.W_CLAMP, ptr(g_emb_c), L._DTYPES[g_emb_c.dtype])
+            w16, w16_epoch = ctx.w16
+            if (gs_bg_full is None and w16 is not None and getattr(w16, "_cor_epoch", -1) == w16_epoch and Cc % 8 == 0 and P % 8 == 0
+                    and os.environ.get("COR_POOL_BWD_GEMM", "1") != "0"):
+                # d emb[b] (C x P) = gs[b]^T (C x M) w[b] (M x P): one batched tcgen05 GEMM on the bf16 weights the forward's
+                # pooling GEMM used (still in their buffer: no later forward of this shape has rewritten them), both operands
+                # MN-major as they lie; the gradient rows are cast to bf16 and zero-padded to a whole 64-row K block, which makes
+                # the other operand's rows beyond M (the ones row, the next image) irrelevant.  Persistent tiles with coalesced
+                # stores: 2-3x faster than the one-shot pool_bwd_umma kernel, which rebuilds both operands from fp32.
+                from .linear import gemm
+                Kp = (M + 63) // 64 * 64
+                a16 = torch.empty((B * Kp, Cc), dtype=torch.bfloat16, device=dev)
+                call("cor_cast_pad_rows_bf16", dev, ptr(gs_fg), B, M, Kp, Cc, ptr(a16))
+                Rp = w16.shape[1]
+                g_emb_c = gemm(a16, w16.view(B * Rp, P), Cc, P, Kp, a_mn=True, b_mn=True, batch=B, a_batch_rows=Kp, b_batch_rows=Rp,
+                               out_dtype=g_emb_c.dtype).view(B, Cc, h, w)
+            else:
+                name = "cor_pool_bwd_umma" if lib.cor_pool_bwd_umma_ok(B, Cc, P, M, int(gs_bg_full is not None)) else "cor_pool_bwd_feat"
+                call(name, dev, ptr(gs_fg), ptr(gs_bg_full), ptr(w32), _ll(P), B, Cc, P, M, ops.W_CLAMP, ptr(g_emb_c), L._DTYPES[g_emb_c.dtype])
             g_emb = g_emb_c.to(emb_dt)
         if side is not None:
             cur.wait_stream(side)

@@ -289,6 +289,9 @@ int cor_gemm_bf16(const void* A, int a_mn, long long a_rows_total, long long a_b
  *                pre_bf16 = pre-activation saved by the GEMM (gelu; the un-scaled linear output for a column scale).
  *                work: cor_act_bwd_work_bytes(M, N) bytes when db or dcolscale is requested. */
 int cor_cast_cat_bf16(const float* a, int c0, const float* b, int c1, long long rows, void* out_bf16, cor_stream_t stream);
+/* out[b][r][:] = bf16(src[b][r][:]) for r < rows, zeros up to rows_padded: a K-padded MN-major GEMM operand (the pooling
+ * backward d feat[b] = gs[b]^T w[b] as one batched cor_gemm_bf16, cor_b200/region.py). cols % 4 == 0. */
+int cor_cast_pad_rows_bf16(const float* src, int batch, int rows, int rows_padded, int cols, void* out_bf16, cor_stream_t stream);
 size_t cor_act_bwd_work_bytes(long long M, int N);
 int cor_act_bwd(const void* dy, int dy_dtype /* f32 or bf16 */, const float* y_f32, const void* pre_bf16, const float* emul,
                 const float* colscale, int act,
