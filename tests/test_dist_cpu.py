@@ -34,9 +34,14 @@ def _worker(rank, ws, port, fn, ret):
 
 def run_ranks(fn, ws=2):
     mgr = mp.Manager()
-    ret = mgr.dict()
-    mp.spawn(_worker, args=(ws, _free_port(), fn, ret), nprocs=ws, join=True)
-    return [ret[r] for r in range(ws)]
+    for attempt in range(2):                 # the probed port can be taken before gloo binds it: one retry on a fresh port
+        ret = mgr.dict()
+        try:
+            mp.spawn(_worker, args=(ws, _free_port(), fn, ret), nprocs=ws, join=True)
+            return [ret[r] for r in range(ws)]
+        except Exception:                     # noqa: BLE001
+            if attempt:
+                raise
 
 
 def _nce_rank(rank, ws):
