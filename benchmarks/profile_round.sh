@@ -11,8 +11,9 @@ B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-graph --
 $B > $OUT/${TAG}_plain_step.log 2>&1 || { echo "plain bench failed"; exit 1; }
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_eager_steps3.csv $B > $OUT/${TAG}_ncu_launches.log 2>&1
 ncu --profile-from-start off --set full --clock-control none --import-source on \
-    -k regex:"mask_prep_staged|pool_umma_kernel|pool_bwd_umma|seg_loss_tile|infonce_bwd_kernel|infonce_tail|fgbg_reduce" -c 7 \
+    -k regex:"mask_prep_staged|pool_umma_kernel|gemm_umma_kernel|seg_loss_tile|infonce_bwd_kernel|infonce_tail|fgbg_reduce" -c 7 \
     -o $OUT/${TAG}_prof_step -f $B > $OUT/${TAG}_ncu_step.log 2>&1
+[ "$2" = "step-only" ] && exit 0
 python benchmarks/one_sim.py 1024 102400 lse > $OUT/${TAG}_plain_sim.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:sim_umma_ts -s 2 -c 1 -o $OUT/${TAG}_prof_sim_ts -f python benchmarks/one_sim.py 1024 102400 lse > $OUT/${TAG}_ncu_sim.log 2>&1
 python benchmarks/one_seg.py 128 > $OUT/${TAG}_plain_seg.log 2>&1 && \
