@@ -62,9 +62,9 @@ class _AdapterTailFn(torch.autograd.Function):
         m32, den, wq, f16 = ctx.saved_tensors
         B, R, P, C, G, Q, Qp, fdt, mdt, fshape, mshape = ctx.cfg
         dev = m32.device
-        g16 = torch.zeros((B, Qp, C), dtype=torch.bfloat16, device=dev)                     # zero rows: Qp is the K extent of d feat
-        g16[:, :Q] = g
-        g16 = g16.view(B * Qp, C)
+        g16 = torch.empty((B * Qp, C), dtype=torch.bfloat16, device=dev)                    # zero rows: Qp is the K extent of d feat
+        g32 = g.float().contiguous()
+        ops._call("cor_cast_pad_rows_bf16", dev, ops.ptr(g32), B, Q, Qp, C, ops.ptr(g16))
         gf = gm = None
         if ctx.needs_input_grad[1]:
             # d feat[b] (C x P) = g[b]^T (C x Q) Wq[b] (Q x P): both operands stored [K = Qp][rows]
